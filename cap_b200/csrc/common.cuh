@@ -1,0 +1,116 @@
+// Shared host-side plumbing of libcapgpu: context, error handling, device buffers.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+#include <map>
+#include <mutex>
+
+#include "../../include/capgpu.h"
+#include "ec.cuh"
+
+namespace capgpu {
+
+struct CudaError {
+  cudaError_t code;
+  const char* file;
+  int line;
+};
+
+#define CAPGPU_CUDA(expr)                                                \
+  do {                                                                   \
+    cudaError_t _e = (expr);                                             \
+    if (_e != cudaSuccess) throw ::capgpu::CudaError{_e, __FILE__, __LINE__}; \
+  } while (0)
+
+struct ArgError { const char* what; };
+#define CAPGPU_REQUIRE(cond, msg) do { if (!(cond)) throw ::capgpu::ArgError{msg}; } while (0)
+struct CodeError { int code; };
+
+// Simple growable device buffer owned by a ctx (stream-ordered frees are not needed: a ctx
+// is single-threaded and buffers live as long as the ctx).
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  void reserve(size_t b) {
+    if (b <= bytes) return;
+    if (p) CAPGPU_CUDA(cudaFree(p));
+    p = nullptr; bytes = 0;
+    CAPGPU_CUDA(cudaMalloc(&p, b));
+    bytes = b;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct NttDomain;  // ntt.cu
+
+}  // namespace capgpu
+
+struct capgpu_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string last_error;
+  uint64_t launches = 0;
+  int sm_count = 148;
+  // NTT domains (twiddle tables), keyed by log_n; owned by the ctx
+  std::map<unsigned, capgpu::NttDomain*> domains;
+  // workspaces
+  capgpu::DevBuf ntt_tmp, ntt_io;
+  capgpu::DevBuf msm_scalars, msm_digits, msm_counts, msm_entries, msm_buckets, msm_partials, msm_out;
+  void* pinned = nullptr;  // small pinned staging area
+  size_t pinned_bytes = 0;
+  // debug view of the last job (device pointers owned by the job workspace)
+  struct capgpu_job* last_job = nullptr;
+  struct capgpu_job* cached_job = nullptr;  // workspace reused across capgpu_prove calls
+};
+
+namespace capgpu {
+
+inline void set_device(const capgpu_ctx* ctx) { CAPGPU_CUDA(cudaSetDevice(ctx->device)); }
+
+// Wraps an ABI entry point: maps exceptions to status codes, records CUDA error text.
+template <class F>
+int guarded(capgpu_ctx* ctx, F&& f) {
+  try {
+    if (ctx) set_device(ctx);
+    f();
+    return CAPGPU_OK;
+  } catch (const CudaError& e) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s (%s) at %s:%d", cudaGetErrorName(e.code), cudaGetErrorString(e.code), e.file, e.line);
+    if (ctx) ctx->last_error = buf;
+    return CAPGPU_ERR_CUDA;
+  } catch (const ArgError& e) {
+    if (ctx) ctx->last_error = e.what;
+    return CAPGPU_ERR_ARG;
+  } catch (const CodeError& e) {
+    return e.code;
+  } catch (const std::bad_alloc&) {
+    if (ctx) ctx->last_error = "host allocation failed";
+    return CAPGPU_ERR_ARG;
+  }
+}
+
+#define CAPGPU_LAUNCH_CHECK(ctx) do { (ctx)->launches++; CAPGPU_CUDA(cudaGetLastError()); } while (0)
+
+inline unsigned ceil_div(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+// ---- ntt.cu -----------------------------------------------------------------------------
+NttDomain* get_domain(capgpu_ctx* ctx, unsigned log_n);
+void destroy_domain(NttDomain* d);
+// dst (batch x n, stride dst_stride) = NTT of src (batch vectors of src_len valid elements,
+// stride src_stride); tmp: scratch of batch x n elements (stride n), may equal dst only for
+// single-pass sizes.  All pointers are device pointers.
+void ntt_device(capgpu_ctx* ctx, unsigned log_n, const Fr* src, size_t src_len, size_t src_stride, Fr* dst,
+                size_t dst_stride, Fr* tmp, size_t batch, bool inverse, bool coset);
+const Fr* domain_omega_powers(capgpu_ctx* ctx, unsigned log_n);  // omega^j, j < n (device)
+
+// ---- msm.cu -----------------------------------------------------------------------------
+// scalars: device, batch vectors of n Fr (stride `stride`); out: device, batch affine points.
+void msm_device(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const Fr* scalars, size_t n, size_t stride,
+                size_t batch, bool scalars_mont, G1Affine* out_dev);
+
+}  // namespace capgpu

@@ -1,0 +1,284 @@
+// 254-bit Montgomery field arithmetic on 8 x 32-bit limbs for BN254 Fr and Fq (sm_100a).
+//
+// Replaces ark-ff 0.3.0 `Fp256<FrParameters>` / `Fp256<FqParameters>` (the field types the
+// reference fixes at /root/reference/src/config.rs:78-83).  Same value representation:
+// little-endian limbs of a*R mod p, R = 2^256, so host buffers of arkworks field elements
+// are usable byte-for-byte (4 x u64 LE == 8 x u32 LE).
+//
+// Multiplication is the even/odd column-split CIOS: the partial products a[j]*b[i] are
+// accumulated as 64-bit wide multiply-adds into two interleaved accumulators (even and odd
+// limb alignment) so that every mad.lo.cc/madc.hi.cc pair lowers to one IMAD.WIDE.U32 with
+// carry-in/out and no separate carry-fold instructions on the ALU pipe.
+//
+// All functions keep values fully reduced in [0, p): results are bit-exact canonical
+// Montgomery residues, which is what the parity tests compare.
+//
+// Host emulation (CAPGPU_HOST_EMU) exists ONLY so tests/cpu_emu can run these exact
+// algorithms against the big-int oracle without a GPU; the product never builds with it.
+#pragma once
+#include <stdint.h>
+
+#if defined(CAPGPU_HOST_EMU) && !defined(__CUDACC__)
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define CAPGPU_EMU 1
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define CAPGPU_DEV 1
+#endif
+
+namespace capgpu {
+
+// ------------------------------------------------------------------------------------------
+// carry-chain primitives
+// ------------------------------------------------------------------------------------------
+#ifdef CAPGPU_DEV
+__device__ __forceinline__ uint32_t add_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("add.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t addc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t addc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("addc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t sub_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("sub.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t subc_cc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.cc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t subc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+// 64-bit wide multiply(-add) on a register pair (lo, hi)
+__device__ __forceinline__ void mul_wide(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+  asm volatile("mul.lo.u32 %0, %2, %3; mul.hi.u32 %1, %2, %3;" : "=&r"(lo), "=r"(hi) : "r"(a), "r"(b));
+}
+// (lo,hi) += a*b, starts a carry chain (no carry-in), leaves carry-out
+__device__ __forceinline__ void mad_wide_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+  asm volatile("mad.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(lo), "+r"(hi) : "r"(a), "r"(b));
+}
+// (lo,hi) += a*b + carry-in, leaves carry-out
+__device__ __forceinline__ void madc_wide_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+  asm volatile("madc.lo.cc.u32 %0, %2, %3, %0; madc.hi.cc.u32 %1, %2, %3, %1;" : "+r"(lo), "+r"(hi) : "r"(a), "r"(b));
+}
+// (lo,hi) = a*b + (clo,chi) + carry-in, leaves carry-out
+__device__ __forceinline__ void madc_wide_cc_to(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b, uint32_t clo, uint32_t chi) {
+  asm volatile("madc.lo.cc.u32 %0, %2, %3, %4; madc.hi.cc.u32 %1, %2, %3, %5;" : "=&r"(lo), "=r"(hi) : "r"(a), "r"(b), "r"(clo), "r"(chi));
+}
+// (lo,hi) = a*b + carry-in, ends the chain (the high word cannot overflow)
+__device__ __forceinline__ void madc_wide_end(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
+  asm volatile("madc.lo.cc.u32 %0, %2, %3, 0; madc.hi.u32 %1, %2, %3, 0;" : "=&r"(lo), "=r"(hi) : "r"(a), "r"(b));
+}
+#else
+// Host emulation of the PTX condition-code semantics (tests only).
+struct EmuCC { static uint32_t& cf() { static thread_local uint32_t c = 0; return c; } };
+inline uint32_t add_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a + b; EmuCC::cf() = (uint32_t)(t >> 32); return (uint32_t)t; }
+inline uint32_t addc_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a + b + EmuCC::cf(); EmuCC::cf() = (uint32_t)(t >> 32); return (uint32_t)t; }
+inline uint32_t addc(uint32_t a, uint32_t b) { return a + b + EmuCC::cf(); }
+inline uint32_t sub_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a - b; EmuCC::cf() = (uint32_t)(t >> 63); return (uint32_t)t; }
+inline uint32_t subc_cc(uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a - b - EmuCC::cf(); EmuCC::cf() = (uint32_t)(t >> 63); return (uint32_t)t; }
+inline uint32_t subc(uint32_t a, uint32_t b) { return a - b - EmuCC::cf(); }
+inline void mul_wide(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) { uint64_t t = (uint64_t)a * b; lo = (uint32_t)t; hi = (uint32_t)(t >> 32); }
+inline void emu_mad(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b, uint32_t clo, uint32_t chi, uint32_t cin, bool cout) {
+  uint64_t p = (uint64_t)a * b;
+  uint64_t l = (uint64_t)(uint32_t)p + clo + cin;
+  uint64_t h = (p >> 32) + chi + (l >> 32);
+  lo = (uint32_t)l; hi = (uint32_t)h;
+  if (cout) EmuCC::cf() = (uint32_t)(h >> 32);
+}
+inline void mad_wide_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) { emu_mad(lo, hi, a, b, lo, hi, 0, true); }
+inline void madc_wide_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) { emu_mad(lo, hi, a, b, lo, hi, EmuCC::cf(), true); }
+inline void madc_wide_cc_to(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b, uint32_t clo, uint32_t chi) { emu_mad(lo, hi, a, b, clo, chi, EmuCC::cf(), true); }
+inline void madc_wide_end(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) { emu_mad(lo, hi, a, b, 0, 0, EmuCC::cf(), false); }
+#endif
+
+// ------------------------------------------------------------------------------------------
+// field parameters (BN254; SURVEY.md App. B, checked against the oracle in tests)
+// ------------------------------------------------------------------------------------------
+struct FrParams {
+  // r = 0x30644e72e131a029b85045b68181585d2833e84879b9709143e1f593f0000001
+  static __host__ __device__ __forceinline__ constexpr uint32_t p(int i) { constexpr uint32_t t[8] = {0xf0000001u, 0x43e1f593u, 0x79b97091u, 0x2833e848u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u}; return t[i]; }
+  static constexpr uint32_t INV = 0xefffffffu;  // -p^-1 mod 2^32
+  static __host__ __device__ __forceinline__ constexpr uint32_t one(int i) { constexpr uint32_t t[8] = {0x4ffffffbu, 0xac96341cu, 0x9f60cd29u, 0x36fc7695u, 0x7879462eu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u}; return t[i]; }  // R mod p
+  static __host__ __device__ __forceinline__ constexpr uint32_t r2(int i) { constexpr uint32_t t[8] = {0xae216da7u, 0x1bb8e645u, 0xe35c59e3u, 0x53fe3ab1u, 0x53bb8085u, 0x8c49833du, 0x7f4e44a5u, 0x0216d0b1u}; return t[i]; }  // R^2 mod p
+};
+struct FqParams {
+  // q = 0x30644e72e131a029b85045b68181585d97816a916871ca8d3c208c16d87cfd47
+  static __host__ __device__ __forceinline__ constexpr uint32_t p(int i) { constexpr uint32_t t[8] = {0xd87cfd47u, 0x3c208c16u, 0x6871ca8du, 0x97816a91u, 0x8181585du, 0xb85045b6u, 0xe131a029u, 0x30644e72u}; return t[i]; }
+  static constexpr uint32_t INV = 0xe4866389u;
+  static __host__ __device__ __forceinline__ constexpr uint32_t one(int i) { constexpr uint32_t t[8] = {0xc58f0d9du, 0xd35d438du, 0xf5c70b3du, 0x0a78eb28u, 0x7879462cu, 0x666ea36fu, 0x9a07df2fu, 0x0e0a77c1u}; return t[i]; }
+  static __host__ __device__ __forceinline__ constexpr uint32_t r2(int i) { constexpr uint32_t t[8] = {0x538afa89u, 0xf32cfc5bu, 0xd44501fbu, 0xb5e71911u, 0x0a417ff6u, 0x47ab1effu, 0xcab8351fu, 0x06d89f71u}; return t[i]; }
+};
+
+template <class PR>
+struct alignas(32) Fp {
+  uint32_t v[8];
+
+  __host__ __device__ __forceinline__ static Fp zero() { Fp r; for (int i = 0; i < 8; i++) r.v[i] = 0; return r; }
+  __host__ __device__ __forceinline__ static Fp one() { Fp r; for (int i = 0; i < 8; i++) r.v[i] = PR::one(i); return r; }
+  __host__ __device__ __forceinline__ static Fp r2() { Fp r; for (int i = 0; i < 8; i++) r.v[i] = PR::r2(i); return r; }
+  __host__ __device__ __forceinline__ bool is_zero() const { uint32_t o = 0; for (int i = 0; i < 8; i++) o |= v[i]; return o == 0; }
+  __host__ __device__ __forceinline__ bool operator==(const Fp& b) const { uint32_t o = 0; for (int i = 0; i < 8; i++) o |= v[i] ^ b.v[i]; return o == 0; }
+  __host__ __device__ __forceinline__ bool operator!=(const Fp& b) const { return !(*this == b); }
+};
+
+// r = a - p if a >= p else a   (a < 2p assumed, given as 8 limbs + no overflow bit)
+template <class PR>
+__host__ __device__ __forceinline__ void fp_final_sub(Fp<PR>& a) {
+  uint32_t t[8];
+  t[0] = sub_cc(a.v[0], PR::p(0));
+#pragma unroll
+  for (int i = 1; i < 8; i++) t[i] = subc_cc(a.v[i], PR::p(i));
+  uint32_t borrow = subc(0, 0);  // 0xffffffff if a < p
+#pragma unroll
+  for (int i = 0; i < 8; i++) a.v[i] = borrow ? a.v[i] : t[i];
+}
+
+template <class PR>
+__host__ __device__ __forceinline__ Fp<PR> fp_add(const Fp<PR>& a, const Fp<PR>& b) {
+  Fp<PR> r;
+  r.v[0] = add_cc(a.v[0], b.v[0]);
+#pragma unroll
+  for (int i = 1; i < 8; i++) r.v[i] = addc_cc(a.v[i], b.v[i]);
+  // p < 2^254 so a + b < 2^255: no carry out of limb 7
+  fp_final_sub(r);
+  return r;
+}
+
+template <class PR>
+__host__ __device__ __forceinline__ Fp<PR> fp_sub(const Fp<PR>& a, const Fp<PR>& b) {
+  Fp<PR> r;
+  r.v[0] = sub_cc(a.v[0], b.v[0]);
+#pragma unroll
+  for (int i = 1; i < 8; i++) r.v[i] = subc_cc(a.v[i], b.v[i]);
+  uint32_t borrow = subc(0, 0);
+  uint32_t t[8];
+  t[0] = add_cc(r.v[0], PR::p(0));
+#pragma unroll
+  for (int i = 1; i < 8; i++) t[i] = addc_cc(r.v[i], PR::p(i));
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = borrow ? t[i] : r.v[i];
+  return r;
+}
+
+template <class PR>
+__host__ __device__ __forceinline__ Fp<PR> fp_neg(const Fp<PR>& a) {
+  Fp<PR> r;
+  r.v[0] = sub_cc(PR::p(0), a.v[0]);
+#pragma unroll
+  for (int i = 1; i < 8; i++) r.v[i] = subc_cc(PR::p(i), a.v[i]);
+  bool z = a.is_zero();
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = z ? 0u : r.v[i];
+  return r;
+}
+
+template <class PR>
+__host__ __device__ __forceinline__ Fp<PR> fp_dbl(const Fp<PR>& a) { return fp_add(a, a); }
+
+// ---- Montgomery multiplication ------------------------------------------------------------
+// X is the accumulator whose word 0 sits at the limb position being reduced in this step,
+// Y the accumulator aligned one limb higher.  After each step the roles swap (the reduced
+// low word of X is dropped, its word 1 is folded into Y[0], words 2.. become the new
+// high accumulator).
+template <class PR>
+__host__ __device__ __forceinline__ void mont_reduce_step(uint32_t* X, uint32_t* Y) {
+  uint32_t m = X[0] * PR::INV;
+  mad_wide_cc(Y[0], Y[1], PR::p(1), m);
+  madc_wide_cc(Y[2], Y[3], PR::p(3), m);
+  madc_wide_cc(Y[4], Y[5], PR::p(5), m);
+  madc_wide_cc(Y[6], Y[7], PR::p(7), m);  // top limb of p < 2^30: no carry out
+  mad_wide_cc(X[0], X[1], PR::p(0), m);
+  madc_wide_cc(X[2], X[3], PR::p(2), m);
+  madc_wide_cc(X[4], X[5], PR::p(4), m);
+  madc_wide_cc(X[6], X[7], PR::p(6), m);
+  Y[7] = addc(Y[7], 0);
+}
+
+template <class PR>
+__host__ __device__ __forceinline__ void mont_mad_row(uint32_t* X, uint32_t* Y, const uint32_t* a, uint32_t bi) {
+  // X: aligned at this row's base position; Y: previous row's X (word 0 is zero, word 1 is
+  // folded into X[0], words 2..7 shift down by two to become the accumulator at base+1).
+  X[0] = add_cc(X[0], Y[1]);
+  madc_wide_cc_to(Y[0], Y[1], a[1], bi, Y[2], Y[3]);
+  madc_wide_cc_to(Y[2], Y[3], a[3], bi, Y[4], Y[5]);
+  madc_wide_cc_to(Y[4], Y[5], a[5], bi, Y[6], Y[7]);
+  madc_wide_end(Y[6], Y[7], a[7], bi);
+  mad_wide_cc(X[0], X[1], a[0], bi);
+  madc_wide_cc(X[2], X[3], a[2], bi);
+  madc_wide_cc(X[4], X[5], a[4], bi);
+  madc_wide_cc(X[6], X[7], a[6], bi);
+  Y[7] = addc(Y[7], 0);
+}
+
+template <class PR>
+__host__ __device__ __forceinline__ Fp<PR> fp_mul(const Fp<PR>& a, const Fp<PR>& b) {
+  uint32_t E[8], O[8];
+  // row 0
+  mul_wide(E[0], E[1], a.v[0], b.v[0]);
+  mul_wide(E[2], E[3], a.v[2], b.v[0]);
+  mul_wide(E[4], E[5], a.v[4], b.v[0]);
+  mul_wide(E[6], E[7], a.v[6], b.v[0]);
+  mul_wide(O[0], O[1], a.v[1], b.v[0]);
+  mul_wide(O[2], O[3], a.v[3], b.v[0]);
+  mul_wide(O[4], O[5], a.v[5], b.v[0]);
+  mul_wide(O[6], O[7], a.v[7], b.v[0]);
+  mont_reduce_step<PR>(E, O);
+#pragma unroll
+  for (int i = 1; i < 8; i += 2) {
+    mont_mad_row<PR>(O, E, a.v, b.v[i]);
+    mont_reduce_step<PR>(O, E);
+    if (i + 1 < 8) {
+      mont_mad_row<PR>(E, O, a.v, b.v[i + 1]);
+      mont_reduce_step<PR>(E, O);
+    }
+  }
+  // after row 7: X = O (aligned at limb 7, word 0 == 0), Y = E (aligned at limb 8)
+  Fp<PR> r;
+  r.v[0] = add_cc(E[0], O[1]);
+#pragma unroll
+  for (int i = 1; i < 7; i++) r.v[i] = addc_cc(E[i], O[i + 1]);
+  r.v[7] = addc(E[7], 0);
+  fp_final_sub(r);
+  return r;
+}
+
+template <class PR>
+__host__ __device__ __forceinline__ Fp<PR> fp_sqr(const Fp<PR>& a) { return fp_mul(a, a); }
+
+// Montgomery -> canonical integer (multiply by 1) and back (multiply by R^2).
+template <class PR>
+__host__ __device__ __forceinline__ Fp<PR> fp_from_mont(const Fp<PR>& a) {
+  Fp<PR> o = Fp<PR>::zero();
+  o.v[0] = 1;
+  return fp_mul(a, o);
+}
+template <class PR>
+__host__ __device__ __forceinline__ Fp<PR> fp_to_mont(const Fp<PR>& a) { return fp_mul(a, Fp<PR>::r2()); }
+
+// a^e for a 256-bit exponent given as 8 LE limbs (square-and-multiply, MSB first).
+template <class PR>
+__host__ __device__ inline Fp<PR> fp_pow(const Fp<PR>& a, const uint32_t* e) {
+  Fp<PR> r = Fp<PR>::one();
+  bool started = false;
+  for (int i = 255; i >= 0; i--) {
+    if (started) r = fp_sqr(r);
+    if ((e[i >> 5] >> (i & 31)) & 1) {
+      r = started ? fp_mul(r, a) : a;
+      started = true;
+    }
+  }
+  return r;
+}
+
+template <class PR>
+__host__ __device__ inline Fp<PR> fp_pow_u64(const Fp<PR>& a, uint64_t e) {
+  uint32_t ee[8] = {(uint32_t)e, (uint32_t)(e >> 32), 0, 0, 0, 0, 0, 0};
+  return fp_pow(a, ee);
+}
+
+// Inversion by Fermat: a^(p-2).  inv(0) = 0 (callers treat zero explicitly).
+template <class PR>
+__host__ __device__ inline Fp<PR> fp_inv(const Fp<PR>& a) {
+  uint32_t e[8];
+  for (int i = 0; i < 8; i++) e[i] = PR::p(i);
+  e[0] -= 2;  // p is odd and p[0] >= 2 for both fields
+  return fp_pow(a, e);
+}
+
+typedef Fp<FrParams> Fr;
+typedef Fp<FqParams> Fq;
+
+}  // namespace capgpu

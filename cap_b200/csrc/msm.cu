@@ -1,0 +1,423 @@
+// Pippenger G1 multi-scalar multiplication over the SRS bases for sm_100a.
+//
+// Replaces ark-ec 0.3.0 `VariableBaseMSM::multi_scalar_mul` as called by ark-poly-commit
+// 0.3.0 `KZG10::commit` for each of the 13 commitments of a proof (reached from
+// /root/reference/src/proof/transfer.rs:181; SRS built at src/proof/mod.rs:59-69).  The
+// result (an affine G1 point) is mathematically unique, so it is bit-identical to arkworks'
+// regardless of the bucket schedule used here:
+//
+//   upload   : bases are fixed per SRS, so the window-shifted copies 2^(c*w) * P_i are
+//              precomputed once (W tables of n affine points).  All W windows of a scalar then
+//              feed ONE set of 2^(c-1) buckets, and no per-window doubling fold remains.
+//   recode   : Montgomery -> canonical, signed c-bit digits d in (-2^(c-1), 2^(c-1)],
+//              per-bucket histogram (global atomics on 2^(c-1) counters).
+//   scan     : exclusive scan of the histogram (one CTA per scalar vector).
+//   scatter  : counting-sort scatter of (table index | sign) entries by bucket.
+//   accumulate: LPB lanes per bucket walk the bucket's entries with XYZZ mixed additions
+//              (8M+2S), then a shuffle tree folds the lanes.
+//   reduce   : sum_k k*B_k by segmented running sums + small scalar multiples, CTA tree, and a
+//              final fold + conversion to affine.
+// `batch` scalar vectors over the same bases (the 5 wire / 5 split-quotient commitments of a
+// round) share every launch (grid.y = vector index).
+#include "common.cuh"
+#include <string.h>
+
+struct capgpu_srs {
+  int device = 0;
+  size_t n = 0;
+  int c = 0, W = 0;
+  size_t K = 0;  // 2^(c-1) buckets
+  capgpu::G1Affine* table = nullptr;  // W x n
+};
+
+namespace capgpu {
+
+// ------------------------------------------------------------------------------------------
+// SRS upload: window-shifted tables
+// ------------------------------------------------------------------------------------------
+__global__ void msm_precompute(G1Affine* table, size_t n, int c, int W) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G1Affine p = table[i];
+  G1XYZZ a = xyzz_from_affine(p);
+  for (int w = 1; w < W; w++) {
+    for (int k = 0; k < c; k++) a = xyzz_dbl(a);
+    G1Affine q = xyzz_to_affine(a);
+    table[(size_t)w * n + i] = q;
+    a = xyzz_from_affine(q);
+  }
+}
+
+// powers_of_g[i] = tau^i * g, g = (1, 2)  (KZG10::setup shape; synthetic SRS)
+__global__ void msm_setup_powers(G1Affine* table, size_t n, Fr tau) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fr s = fp_from_mont(fp_pow_u64(tau, i));
+  G1Affine g;
+  g.x = Fq::one();
+  g.y = fp_dbl(Fq::one());
+  G1XYZZ acc = G1XYZZ::inf();
+  bool started = false;
+  for (int b = 253; b >= 0; b--) {
+    if (started) acc = xyzz_dbl(acc);
+    if ((s.v[b >> 5] >> (b & 31)) & 1) { xyzz_add_mixed(acc, g.x, g.y, false); started = true; }
+  }
+  table[i] = xyzz_to_affine(acc);
+}
+
+// ------------------------------------------------------------------------------------------
+// recode + histogram
+// ------------------------------------------------------------------------------------------
+__global__ void msm_recode(const Fr* scalars, size_t n, size_t stride, int mont, int c, int W, int32_t* digits,
+                           uint32_t* counts, size_t K) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const size_t b = blockIdx.y;
+  Fr s = scalars[b * stride + i];
+  if (mont) s = fp_from_mont(s);
+  const uint32_t mask = (1u << c) - 1u;
+  const int32_t half = 1 << (c - 1);
+  int32_t carry = 0;
+  uint32_t* cnt = counts + b * (K + 2);
+  for (int w = 0; w < W; w++) {
+    uint32_t off = (uint32_t)(w * c);
+    uint32_t limb = off >> 5, sh = off & 31;
+    uint32_t v = 0;
+    if (limb < 8) {
+      v = s.v[limb] >> sh;
+      if (sh + c > 32 && limb + 1 < 8) v |= s.v[limb + 1] << (32 - sh);
+      v &= mask;
+    }
+    int32_t d = (int32_t)v + carry;
+    carry = 0;
+    if (d > half) { d -= (1 << c); carry = 1; }
+    digits[(b * W + w) * n + i] = d;
+    if (d != 0) atomicAdd(&cnt[d < 0 ? -d : d], 1u);
+  }
+}
+
+// counts[b][0..K] -> exclusive offsets in place (entry K+1 = total); cursors = copy.
+__global__ void msm_scan(uint32_t* counts, uint32_t* cursors, size_t K) {
+  __shared__ uint32_t warp_sums[32];
+  __shared__ uint32_t carry_s;
+  uint32_t* cnt = counts + (size_t)blockIdx.x * (K + 2);
+  uint32_t* cur = cursors + (size_t)blockIdx.x * (K + 2);
+  const size_t total = K + 2;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (size_t base = 0; base < total; base += blockDim.x) {
+    size_t idx = base + threadIdx.x;
+    uint32_t v = (idx < K + 1) ? cnt[idx] : 0u;
+    // inclusive warp scan
+    uint32_t x = v;
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if ((threadIdx.x & 31) >= o) x += y;
+    }
+    if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = x;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      uint32_t ws = (threadIdx.x < (blockDim.x >> 5)) ? warp_sums[threadIdx.x] : 0u;
+      uint32_t z = ws;
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, z, o);
+        if (threadIdx.x >= o) z += y;
+      }
+      warp_sums[threadIdx.x] = z - ws;  // exclusive
+    }
+    __syncthreads();
+    uint32_t excl = carry_s + warp_sums[threadIdx.x >> 5] + x - v;
+    if (idx < total) { cnt[idx] = excl; cur[idx] = excl; }
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry_s = excl + v;
+    __syncthreads();
+  }
+}
+
+__global__ void msm_scatter(const int32_t* digits, size_t n, int W, uint32_t* cursors, uint32_t* entries, size_t K,
+                            size_t table_n, size_t base_off) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const size_t w = blockIdx.y, b = blockIdx.z;
+  int32_t d = digits[(b * W + w) * n + i];
+  if (d == 0) return;
+  uint32_t k = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+  uint32_t pos = atomicAdd(&cursors[b * (K + 2) + k], 1u);
+  uint32_t idx = (uint32_t)(w * table_n + base_off + i);
+  entries[b * ((size_t)W * n) + pos] = idx | (d < 0 ? 0x80000000u : 0u);
+}
+
+// ------------------------------------------------------------------------------------------
+// bucket accumulation
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ G1XYZZ shfl_down_xyzz(const G1XYZZ& p, int delta, int width) {
+  G1XYZZ r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    r.X.v[i] = __shfl_down_sync(0xffffffffu, p.X.v[i], delta, width);
+    r.Y.v[i] = __shfl_down_sync(0xffffffffu, p.Y.v[i], delta, width);
+    r.ZZ.v[i] = __shfl_down_sync(0xffffffffu, p.ZZ.v[i], delta, width);
+    r.ZZZ.v[i] = __shfl_down_sync(0xffffffffu, p.ZZZ.v[i], delta, width);
+  }
+  return r;
+}
+
+template <int LPB>
+__global__ void __launch_bounds__(128) msm_accumulate(const G1Affine* __restrict__ table, const uint32_t* __restrict__ entries,
+                                                      const uint32_t* __restrict__ offsets, G1XYZZ* buckets, size_t K,
+                                                      size_t entries_stride) {
+  const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t bucket = gid / LPB;
+  const uint32_t lane = (uint32_t)(gid % LPB);
+  const size_t b = blockIdx.y;
+  G1XYZZ acc = G1XYZZ::inf();
+  if (bucket < K) {
+    const uint32_t* off = offsets + b * (K + 2);
+    uint32_t start = off[bucket + 1], end = off[bucket + 2];
+    const uint32_t* ent = entries + b * entries_stride;
+    for (uint32_t e = start + lane; e < end; e += LPB) {
+      uint32_t u = ent[e];
+      G1Affine p = table[u & 0x7fffffffu];
+      if (!p.is_inf()) xyzz_add_mixed(acc, p.x, p.y, (u >> 31) != 0);
+    }
+  }
+  if (LPB > 1) {
+#pragma unroll
+    for (int o = LPB / 2; o > 0; o >>= 1) {
+      G1XYZZ other = shfl_down_xyzz(acc, o, LPB);
+      xyzz_add(acc, other);
+    }
+  }
+  if (bucket < K && lane == 0) buckets[b * K + bucket] = acc;
+}
+
+// ------------------------------------------------------------------------------------------
+// bucket reduction: sum_{k'=0}^{K-1} (k'+1) * B[k']
+// ------------------------------------------------------------------------------------------
+__device__ inline G1XYZZ block_reduce_xyzz(G1XYZZ v, G1XYZZ* smem /* >= 32 entries */) {
+  for (int o = 16; o > 0; o >>= 1) {
+    G1XYZZ other = shfl_down_xyzz(v, o, 32);
+    xyzz_add(v, other);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (blockDim.x + 31) >> 5;
+  if (lane == 0) smem[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    v = lane < nwarps ? smem[lane] : G1XYZZ::inf();
+    for (int o = 16; o > 0; o >>= 1) {
+      G1XYZZ other = shfl_down_xyzz(v, o, 32);
+      xyzz_add(v, other);
+    }
+  }
+  return v;  // valid in thread 0
+}
+
+__global__ void __launch_bounds__(256) msm_reduce_segments(const G1XYZZ* __restrict__ buckets, size_t K, uint32_t L,
+                                                           G1XYZZ* partials) {
+  __shared__ G1XYZZ smem[32];
+  const size_t T = K / L;
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t b = blockIdx.y;
+  G1XYZZ v = G1XYZZ::inf();
+  if (t < T) {
+    const G1XYZZ* B = buckets + b * K;
+    G1XYZZ running = G1XYZZ::inf(), acc = G1XYZZ::inf();
+    for (size_t k = (t + 1) * L; k-- > t * L;) {
+      G1XYZZ q = B[k];
+      xyzz_add(running, q);
+      xyzz_add(acc, running);
+    }
+    v = xyzz_mul_small(running, (uint32_t)(t * L));
+    xyzz_add(v, acc);
+  }
+  v = block_reduce_xyzz(v, smem);
+  if (threadIdx.x == 0) partials[b * gridDim.x + blockIdx.x] = v;
+}
+
+__global__ void msm_finalize(const G1XYZZ* partials, uint32_t nparts, G1Affine* out) {
+  const size_t b = blockIdx.x;
+  G1XYZZ v = G1XYZZ::inf();
+  for (uint32_t i = threadIdx.x; i < nparts; i += 32) {
+    G1XYZZ q = partials[b * nparts + i];
+    xyzz_add(v, q);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    G1XYZZ other = shfl_down_xyzz(v, o, 32);
+    xyzz_add(v, other);
+  }
+  if (threadIdx.x == 0) out[b] = xyzz_to_affine(v);
+}
+
+// ------------------------------------------------------------------------------------------
+// host driver
+// ------------------------------------------------------------------------------------------
+static int ceil_log2(size_t x) { int l = 0; while (((size_t)1 << l) < x) l++; return l; }
+
+template <int LPB>
+static void launch_accumulate(capgpu_ctx* ctx, const capgpu_srs* srs, const uint32_t* entries, const uint32_t* offsets,
+                              G1XYZZ* buckets, size_t entries_stride, size_t batch) {
+  size_t threads = srs->K * LPB;
+  dim3 grid(ceil_div(threads, 128), (unsigned)batch);
+  msm_accumulate<LPB><<<grid, 128, 0, ctx->stream>>>(srs->table, entries, offsets, buckets, srs->K, entries_stride);
+  CAPGPU_LAUNCH_CHECK(ctx);
+}
+
+void msm_device(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const Fr* scalars, size_t n, size_t stride,
+                size_t batch, bool scalars_mont, G1Affine* out_dev) {
+  if (batch == 0) return;
+  if (base_off + n > srs->n) throw CodeError{CAPGPU_ERR_SRS_TOO_SMALL};
+  CAPGPU_REQUIRE(srs->device == ctx->device, "SRS lives on another device");
+  const size_t K = srs->K;
+  const int W = srs->W, c = srs->c;
+  if (n == 0) {
+    CAPGPU_CUDA(cudaMemsetAsync(out_dev, 0, batch * sizeof(G1Affine), ctx->stream));
+    return;
+  }
+  ctx->msm_digits.reserve(batch * W * n * sizeof(int32_t));
+  ctx->msm_counts.reserve(2 * batch * (K + 2) * sizeof(uint32_t));
+  ctx->msm_entries.reserve(batch * W * n * sizeof(uint32_t));
+  ctx->msm_buckets.reserve(batch * K * sizeof(G1XYZZ));
+  int32_t* digits = ctx->msm_digits.as<int32_t>();
+  uint32_t* counts = ctx->msm_counts.as<uint32_t>();
+  uint32_t* cursors = counts + batch * (K + 2);
+  uint32_t* entries = ctx->msm_entries.as<uint32_t>();
+  G1XYZZ* buckets = ctx->msm_buckets.as<G1XYZZ>();
+
+  CAPGPU_CUDA(cudaMemsetAsync(counts, 0, batch * (K + 2) * sizeof(uint32_t), ctx->stream));
+  {
+    dim3 grid(ceil_div(n, 128), (unsigned)batch);
+    msm_recode<<<grid, 128, 0, ctx->stream>>>(scalars, n, stride, scalars_mont ? 1 : 0, c, W, digits, counts, K);
+    CAPGPU_LAUNCH_CHECK(ctx);
+  }
+  msm_scan<<<(unsigned)batch, 1024, 0, ctx->stream>>>(counts, cursors, K);
+  CAPGPU_LAUNCH_CHECK(ctx);
+  {
+    dim3 grid(ceil_div(n, 256), (unsigned)W, (unsigned)batch);
+    msm_scatter<<<grid, 256, 0, ctx->stream>>>(digits, n, W, cursors, entries, K, srs->n, base_off);
+    CAPGPU_LAUNCH_CHECK(ctx);
+  }
+  // lanes per bucket: aim for ~128k accumulating threads
+  size_t lpb = 1;
+  while (lpb < 32 && batch * K * lpb * 2 <= 131072) lpb <<= 1;
+  const size_t es = (size_t)W * n;
+  switch (lpb) {
+    case 1: launch_accumulate<1>(ctx, srs, entries, counts, buckets, es, batch); break;
+    case 2: launch_accumulate<2>(ctx, srs, entries, counts, buckets, es, batch); break;
+    case 4: launch_accumulate<4>(ctx, srs, entries, counts, buckets, es, batch); break;
+    case 8: launch_accumulate<8>(ctx, srs, entries, counts, buckets, es, batch); break;
+    case 16: launch_accumulate<16>(ctx, srs, entries, counts, buckets, es, batch); break;
+    default: launch_accumulate<32>(ctx, srs, entries, counts, buckets, es, batch); break;
+  }
+  // segmented reduction
+  uint32_t L = (uint32_t)(K / 256);
+  if (L < 1) L = 1;
+  if (L > 16) L = 16;
+  size_t T = K / L;
+  unsigned block = T >= 256 ? 256 : (T < 32 ? 32 : (unsigned)T);
+  unsigned nblocks = ceil_div(T, block);
+  ctx->msm_partials.reserve(batch * nblocks * sizeof(G1XYZZ));
+  G1XYZZ* partials = ctx->msm_partials.as<G1XYZZ>();
+  {
+    dim3 grid(nblocks, (unsigned)batch);
+    msm_reduce_segments<<<grid, block, 0, ctx->stream>>>(buckets, K, L, partials);
+    CAPGPU_LAUNCH_CHECK(ctx);
+  }
+  msm_finalize<<<(unsigned)batch, 32, 0, ctx->stream>>>(partials, nblocks, out_dev);
+  CAPGPU_LAUNCH_CHECK(ctx);
+}
+
+}  // namespace capgpu
+
+using namespace capgpu;
+
+static int srs_create(capgpu_ctx* ctx, const uint64_t* points_xy, const uint64_t* tau, size_t n_points, int window_bits, capgpu_srs** out);
+
+extern "C" int capgpu_srs_upload(capgpu_ctx* ctx, const uint64_t* points_xy, size_t n_points, int window_bits, capgpu_srs** out) {
+  if (!ctx || !out || !points_xy) return CAPGPU_ERR_ARG;
+  return srs_create(ctx, points_xy, nullptr, n_points, window_bits, out);
+}
+
+extern "C" int capgpu_srs_setup(capgpu_ctx* ctx, const uint64_t* tau, size_t n_points, int window_bits, capgpu_srs** out) {
+  if (!ctx || !out || !tau) return CAPGPU_ERR_ARG;
+  return srs_create(ctx, nullptr, tau, n_points, window_bits, out);
+}
+
+extern "C" int capgpu_srs_export(capgpu_ctx* ctx, const capgpu_srs* srs, uint64_t* points_xy, size_t n_points) {
+  if (!ctx || !srs || !points_xy) return CAPGPU_ERR_ARG;
+  return guarded(ctx, [&] {
+    CAPGPU_REQUIRE(n_points <= srs->n, "export larger than the SRS");
+    CAPGPU_CUDA(cudaMemcpyAsync(points_xy, srs->table, n_points * sizeof(G1Affine), cudaMemcpyDeviceToHost, ctx->stream));
+    CAPGPU_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+static int srs_create(capgpu_ctx* ctx, const uint64_t* points_xy, const uint64_t* tau, size_t n_points, int window_bits, capgpu_srs** out) {
+  *out = nullptr;
+  capgpu_srs* srs = new capgpu_srs();
+  int rc = guarded(ctx, [&] {
+    CAPGPU_REQUIRE(n_points >= 1 && n_points <= ((size_t)1 << 21), "SRS size out of range");
+    int c = window_bits;
+    if (c == 0) {
+      c = ceil_log2(n_points) + 1;
+      if (c > 16) c = 16;
+      if (c < 4) c = 4;
+    }
+    CAPGPU_REQUIRE(c >= 2 && c <= 16, "window_bits must be in [2, 16]");
+    srs->device = ctx->device;
+    srs->n = n_points;
+    srs->c = c;
+    srs->W = (255 + c - 1) / c;
+    srs->K = (size_t)1 << (c - 1);
+    CAPGPU_REQUIRE((size_t)srs->W * n_points < ((size_t)1 << 31), "SRS too large for 31-bit table indices");
+    CAPGPU_CUDA(cudaMalloc(&srs->table, (size_t)srs->W * n_points * sizeof(G1Affine)));
+    if (points_xy) {
+      CAPGPU_CUDA(cudaMemcpyAsync(srs->table, points_xy, n_points * sizeof(G1Affine), cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+      Fr t;
+      memcpy(t.v, tau, sizeof t.v);
+      msm_setup_powers<<<ceil_div(n_points, 64), 64, 0, ctx->stream>>>(srs->table, n_points, t);
+      CAPGPU_LAUNCH_CHECK(ctx);
+    }
+    msm_precompute<<<ceil_div(n_points, 64), 64, 0, ctx->stream>>>(srs->table, n_points, srs->c, srs->W);
+    CAPGPU_LAUNCH_CHECK(ctx);
+    CAPGPU_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+  if (rc != CAPGPU_OK) {
+    if (srs->table) cudaFree(srs->table);
+    delete srs;
+    return rc;
+  }
+  *out = srs;
+  return CAPGPU_OK;
+}
+
+extern "C" void capgpu_srs_destroy(capgpu_srs* srs) {
+  if (!srs) return;
+  cudaSetDevice(srs->device);
+  if (srs->table) cudaFree(srs->table);
+  delete srs;
+}
+
+extern "C" size_t capgpu_srs_size(const capgpu_srs* srs) { return srs ? srs->n : 0; }
+
+extern "C" int capgpu_msm_g1(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const uint64_t* scalars, size_t n,
+                             size_t batch, int scalars_mont, uint64_t* out_xy) {
+  if (!ctx || !srs || !out_xy || (!scalars && n)) return CAPGPU_ERR_ARG;
+  return guarded(ctx, [&] {
+    ctx->msm_scalars.reserve((batch * n + 1) * sizeof(Fr));
+    ctx->msm_out.reserve(batch * sizeof(G1Affine));
+    if (n) CAPGPU_CUDA(cudaMemcpyAsync(ctx->msm_scalars.p, scalars, batch * n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+    msm_device(ctx, srs, base_off, ctx->msm_scalars.as<Fr>(), n, n, batch, scalars_mont != 0, ctx->msm_out.as<G1Affine>());
+    CAPGPU_CUDA(cudaMemcpyAsync(out_xy, ctx->msm_out.p, batch * sizeof(G1Affine), cudaMemcpyDeviceToHost, ctx->stream));
+    CAPGPU_CUDA(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+extern "C" int capgpu_msm_g1_dev(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const void* d_scalars, size_t n,
+                                 size_t batch, int scalars_mont, void* d_out_xy) {
+  if (!ctx || !srs || !d_out_xy || (!d_scalars && n)) return CAPGPU_ERR_ARG;
+  return guarded(ctx, [&] {
+    msm_device(ctx, srs, base_off, (const Fr*)d_scalars, n, n, batch, scalars_mont != 0, (G1Affine*)d_out_xy);
+  });
+}

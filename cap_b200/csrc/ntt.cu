@@ -1,0 +1,293 @@
+// Radix-2 NTT / INTT / coset NTT over BN254 Fr for sm_100a.
+//
+// Replaces ark-poly 0.3.0 `Radix2EvaluationDomain::{fft, ifft, coset_fft, coset_ifft}` (natural
+// order in and out, generator omega_n = 5^((r-1)/n), coset shift 5), the transforms behind
+// jf-relation's compute_wire_polynomials / compute_prod_permutation_polynomial and jf-plonk's
+// compute_quotient_polynomial, all reached from /root/reference/src/proof/transfer.rs:181.
+//
+// Decomposition: n = R*C (R = 2^ceil(log n / 2) <= 1024, C = n/R).  With j = j1*C + j2 and
+// i = i1 + R*i2,
+//     X[i1 + R*i2] = sum_j2 w_C^(j2 i2) * [ w_n^(j2 i1) * sum_j1 x[j1*C + j2] w_R^(j1 i1) ].
+// Pass 1 runs the R-point column transforms (G adjacent columns per CTA, 1024 elements in
+// shared memory, limb-planar), multiplies by the `mid` table (w_n^(j2 i1), with the coset
+// power g^j2 and the 1/n of an inverse transform folded in) and stores in place; pass 2 runs
+// the C-point row transforms and writes the natural-order result.  The coset shift of the
+// input is the R-entry `pre` table ((g^C)^j1); the g^-i / n scaling of coset_ifft is the
+// `post` table.  n <= 1024 is a single pass.  Inputs shorter than n are zero-extended on
+// load (the 8n-point quotient-domain transforms read only n+3 coefficients).
+//
+// Roofline: a size-n transform costs (n/2) log2 n butterflies = one Montgomery product each
+// (136 IMAD.WIDE) plus <= 2 table products per element, against 2 * 32 B * n of HBM traffic
+// per pass; at the prover's sizes it is bound by the integer pipe, not HBM.
+#include "common.cuh"
+
+namespace capgpu {
+
+static __device__ __constant__ uint32_t kRoot28[8] = {0x80d13d9cu, 0x636e7355u, 0x2445ffd6u, 0xa22bf374u, 0x1eb203d8u, 0x56452ac0u, 0x2963f9e7u, 0x1860ef94u};
+static __device__ __constant__ uint32_t kRoot28Inv[8] = {0x584bb683u, 0x89bcc016u, 0x0164a50cu, 0xe8d9887fu, 0x795eda3du, 0x755e95cbu, 0x1323b130u, 0x0f572b87u};
+static __device__ __constant__ uint32_t kGen[8] = {0x9fffffe6u, 0x1b0d0ef9u, 0xa32a913fu, 0xeaba68a3u, 0xd8dd0689u, 0x47d8eb76u, 0x20f5bbc3u, 0x15d00855u};
+static __device__ __constant__ uint32_t kGenInv[8] = {0x09999999u, 0xd7453974u, 0x83c3efa8u, 0xb4ada7d4u, 0xe57f3161u, 0xc49ca2f8u, 0xac156cb3u, 0x162a3754u};
+static __device__ __constant__ uint32_t kInv2[8] = {0x1ffffffeu, 0x783c14d8u, 0x0c8d1eddu, 0xaf982f6fu, 0xfcfd4f45u, 0x8f5f7492u, 0x3d9cbfacu, 0x1f37631au};
+
+struct NttVariant {
+  Fr* pre = nullptr;
+  Fr* mid = nullptr;
+  Fr* post = nullptr;
+  bool built = false;
+};
+
+struct NttDomain {
+  unsigned log_n = 0, log_r = 0, log_c = 0;
+  size_t n = 0;
+  Fr* tile_tw[2] = {nullptr, nullptr};  // w_1024^k and w_1024^-k, k < 512
+  NttVariant var[2][2];                 // [inverse][coset]
+  Fr* omega_pows = nullptr;             // w_n^j, j < n (built on demand)
+};
+
+__device__ __forceinline__ Fr load_const(const uint32_t* c) {
+  Fr r;
+#pragma unroll
+  for (int i = 0; i < 8; i++) r.v[i] = c[i];
+  return r;
+}
+
+// base^(2^k)
+__device__ inline Fr sqr_times(Fr x, unsigned k) {
+  for (unsigned i = 0; i < k; i++) x = fp_sqr(x);
+  return x;
+}
+
+// Table element kinds.  Every entry is one or two small powers, computed independently per
+// thread (tables are built once per domain size and cached in the ctx).
+enum TableKind {
+  TBL_TILE_FWD = 0,   // w_1024^k
+  TBL_TILE_INV = 1,   // w_1024^-k
+  TBL_OMEGA = 2,      // w_n^j
+  TBL_MID = 3,        // [g^j2] * w_n^(+-j2*i1) [* 1/n]   index = i1*C + j2
+  TBL_PRE = 4,        // (g^C)^j1
+  TBL_POST = 5,       // [g^-i] / n
+};
+
+__global__ void ntt_build_table(Fr* out, size_t count, int kind, unsigned log_n, unsigned log_c, int inverse, int coset) {
+  size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= count) return;
+  Fr root = load_const(inverse ? kRoot28Inv : kRoot28);
+  Fr v;
+  switch (kind) {
+    case TBL_TILE_FWD:
+    case TBL_TILE_INV: {
+      Fr w = sqr_times(load_const(kind == TBL_TILE_INV ? kRoot28Inv : kRoot28), 28 - 10);
+      v = fp_pow_u64(w, idx);
+      break;
+    }
+    case TBL_OMEGA: {
+      Fr w = sqr_times(load_const(kRoot28), 28 - log_n);
+      v = fp_pow_u64(w, idx);
+      break;
+    }
+    case TBL_MID: {
+      uint64_t c_mask = ((uint64_t)1 << log_c) - 1;
+      uint64_t j2 = idx & c_mask, i1 = idx >> log_c;
+      Fr w = sqr_times(root, 28 - log_n);
+      v = fp_pow_u64(w, j2 * i1);
+      if (coset && !inverse) v = fp_mul(v, fp_pow_u64(load_const(kGen), j2));
+      if (inverse && !coset) v = fp_mul(v, fp_pow_u64(load_const(kInv2), log_n));
+      break;
+    }
+    case TBL_PRE: {
+      Fr gc = sqr_times(load_const(kGen), log_c);
+      v = fp_pow_u64(gc, idx);
+      break;
+    }
+    case TBL_POST: {
+      v = fp_pow_u64(load_const(kInv2), log_n);
+      if (coset) v = fp_mul(v, fp_pow_u64(load_const(kGenInv), idx));
+      break;
+    }
+    default:
+      v = Fr::zero();
+  }
+  out[idx] = v;
+}
+
+static Fr* build_table(capgpu_ctx* ctx, size_t count, int kind, unsigned log_n, unsigned log_c, int inverse, int coset) {
+  Fr* p = nullptr;
+  CAPGPU_CUDA(cudaMalloc(&p, count * sizeof(Fr)));
+  ntt_build_table<<<ceil_div(count, 128), 128, 0, ctx->stream>>>(p, count, kind, log_n, log_c, inverse, coset);
+  CAPGPU_LAUNCH_CHECK(ctx);
+  return p;
+}
+
+NttDomain* get_domain(capgpu_ctx* ctx, unsigned log_n) {
+  auto it = ctx->domains.find(log_n);
+  if (it != ctx->domains.end()) return it->second;
+  CAPGPU_REQUIRE(log_n >= 1 && log_n <= 20, "NTT size must be 2^1 .. 2^20");
+  NttDomain* d = new NttDomain();
+  d->log_n = log_n;
+  d->n = (size_t)1 << log_n;
+  if (log_n <= 10) { d->log_r = log_n; d->log_c = 0; }
+  else { d->log_r = (log_n + 1) / 2; d->log_c = log_n - d->log_r; }
+  d->tile_tw[0] = build_table(ctx, 512, TBL_TILE_FWD, log_n, 0, 0, 0);
+  d->tile_tw[1] = build_table(ctx, 512, TBL_TILE_INV, log_n, 0, 1, 0);
+  ctx->domains[log_n] = d;
+  return d;
+}
+
+static void build_variant(capgpu_ctx* ctx, NttDomain* d, bool inverse, bool coset) {
+  NttVariant& v = d->var[inverse][coset];
+  if (v.built) return;
+  bool two_pass = d->log_c > 0;
+  if (two_pass) v.mid = build_table(ctx, d->n, TBL_MID, d->log_n, d->log_c, inverse, coset);
+  if (coset && !inverse) v.pre = build_table(ctx, (size_t)1 << d->log_r, TBL_PRE, d->log_n, d->log_c, 0, 1);
+  if (inverse && (coset || !two_pass)) v.post = build_table(ctx, d->n, TBL_POST, d->log_n, d->log_c, 1, coset);
+  v.built = true;
+}
+
+const Fr* domain_omega_powers(capgpu_ctx* ctx, unsigned log_n) {
+  NttDomain* d = get_domain(ctx, log_n);
+  if (!d->omega_pows) d->omega_pows = build_table(ctx, d->n, TBL_OMEGA, log_n, 0, 0, 0);
+  return d->omega_pows;
+}
+
+void destroy_domain(NttDomain* d) {
+  if (!d) return;
+  for (int i = 0; i < 2; i++) {
+    if (d->tile_tw[i]) cudaFree(d->tile_tw[i]);
+    for (int c = 0; c < 2; c++) {
+      if (d->var[i][c].pre) cudaFree(d->var[i][c].pre);
+      if (d->var[i][c].mid) cudaFree(d->var[i][c].mid);
+      if (d->var[i][c].post) cudaFree(d->var[i][c].post);
+    }
+  }
+  if (d->omega_pows) cudaFree(d->omega_pows);
+  delete d;
+}
+
+// ------------------------------------------------------------------------------------------
+// tile kernel
+// ------------------------------------------------------------------------------------------
+struct NttPass {
+  const Fr* src;
+  Fr* dst;
+  size_t src_stride, dst_stride;
+  uint32_t src_len;
+  uint32_t log_t, log_g;
+  uint32_t in_p_stride, in_g_stride, out_q_stride, out_g_stride;
+  const Fr* pre;
+  const Fr* post;
+  const Fr* tw;
+};
+
+__device__ __forceinline__ Fr smem_load(const uint32_t* s, uint32_t plane, uint32_t e) {
+  Fr r;
+#pragma unroll
+  for (int l = 0; l < 8; l++) r.v[l] = s[l * plane + e];
+  return r;
+}
+__device__ __forceinline__ void smem_store(uint32_t* s, uint32_t plane, uint32_t e, const Fr& x) {
+#pragma unroll
+  for (int l = 0; l < 8; l++) s[l * plane + e] = x.v[l];
+}
+
+__global__ void __launch_bounds__(512) ntt_tile_kernel(NttPass P) {
+  extern __shared__ uint32_t smem[];
+  const uint32_t T = 1u << P.log_t, G = 1u << P.log_g, E = T * G;
+  const uint32_t PAD = G > 1 ? (32u / G ? 32u / G : 1u) : 0u;
+  const uint32_t TS = T + PAD;
+  const uint32_t plane = G * TS;
+  const uint32_t gbase = blockIdx.x * G;
+  const Fr* src = P.src + (size_t)blockIdx.y * P.src_stride;
+  Fr* dst = P.dst + (size_t)blockIdx.y * P.dst_stride;
+
+  for (uint32_t ld = threadIdx.x; ld < E; ld += blockDim.x) {
+    uint32_t p, g;
+    if (P.in_p_stride == 1) { p = ld & (T - 1); g = ld >> P.log_t; }
+    else { g = ld & (G - 1); p = ld >> P.log_g; }
+    uint32_t idx = p * P.in_p_stride + (gbase + g) * P.in_g_stride;
+    Fr x;
+    if (idx < P.src_len) {
+      x = src[idx];
+      if (P.pre) x = fp_mul(x, P.pre[p]);
+    } else {
+      x = Fr::zero();
+    }
+    smem_store(smem, plane, g * TS + p, x);
+  }
+  __syncthreads();
+
+  for (uint32_t s = 0; s < P.log_t; s++) {
+    const uint32_t log_m = P.log_t - 1 - s;
+    const uint32_t m = 1u << log_m;
+    for (uint32_t t = threadIdx.x; t < E / 2; t += blockDim.x) {
+      uint32_t g = t >> (P.log_t - 1);
+      uint32_t tt = t & (T / 2 - 1);
+      uint32_t k = tt & (m - 1);
+      uint32_t p0 = ((tt >> log_m) << (log_m + 1)) + k;
+      uint32_t e0 = g * TS + p0, e1 = e0 + m;
+      Fr u = smem_load(smem, plane, e0);
+      Fr v = smem_load(smem, plane, e1);
+      smem_store(smem, plane, e0, fp_add(u, v));
+      Fr d = fp_sub(u, v);
+      if (log_m > 0) d = fp_mul(d, P.tw[k << (9 - log_m)]);
+      smem_store(smem, plane, e1, d);
+    }
+    __syncthreads();
+  }
+
+  for (uint32_t st = threadIdx.x; st < E; st += blockDim.x) {
+    uint32_t g = st & (G - 1), q = st >> P.log_g;
+    uint32_t p = P.log_t ? (__brev(q) >> (32 - P.log_t)) : 0;
+    Fr x = smem_load(smem, plane, g * TS + p);
+    uint32_t oidx = q * P.out_q_stride + (gbase + g) * P.out_g_stride;
+    if (P.post) x = fp_mul(x, P.post[oidx]);
+    dst[oidx] = x;
+  }
+}
+
+static void launch_pass(capgpu_ctx* ctx, const NttPass& p, size_t n, size_t batch) {
+  uint32_t T = 1u << p.log_t, G = 1u << p.log_g, E = T * G;
+  uint32_t PAD = G > 1 ? (32u / G ? 32u / G : 1u) : 0u;
+  size_t smem = (size_t)8 * G * (T + PAD) * sizeof(uint32_t);
+  unsigned threads = E / 2 >= 512 ? 512 : (E / 2 < 32 ? 32 : E / 2);
+  dim3 grid((unsigned)(n / E), (unsigned)batch);
+  ntt_tile_kernel<<<grid, threads, smem, ctx->stream>>>(p);
+  CAPGPU_LAUNCH_CHECK(ctx);
+}
+
+void ntt_device(capgpu_ctx* ctx, unsigned log_n, const Fr* src, size_t src_len, size_t src_stride, Fr* dst,
+                size_t dst_stride, Fr* tmp, size_t batch, bool inverse, bool coset) {
+  NttDomain* d = get_domain(ctx, log_n);
+  build_variant(ctx, d, inverse, coset);
+  const NttVariant& v = d->var[inverse][coset];
+  CAPGPU_REQUIRE(src_len <= d->n, "NTT input longer than the domain");
+  if (batch == 0) return;
+  NttPass p;
+  p.tw = d->tile_tw[inverse ? 1 : 0];
+  p.src_len = (uint32_t)src_len;
+  if (d->log_c == 0) {
+    p.src = src; p.dst = dst; p.src_stride = src_stride; p.dst_stride = dst_stride;
+    p.log_t = log_n; p.log_g = 0;
+    p.in_p_stride = 1; p.in_g_stride = 0; p.out_q_stride = 1; p.out_g_stride = 0;
+    p.pre = v.pre; p.post = v.post;
+    launch_pass(ctx, p, d->n, batch);
+    return;
+  }
+  const uint32_t R = 1u << d->log_r, C = 1u << d->log_c;
+  // pass 1: columns
+  p.src = src; p.dst = tmp; p.src_stride = src_stride; p.dst_stride = d->n;
+  p.log_t = d->log_r; p.log_g = 10 - d->log_r;
+  if ((1u << p.log_g) > C) p.log_g = d->log_c;
+  p.in_p_stride = C; p.in_g_stride = 1; p.out_q_stride = C; p.out_g_stride = 1;
+  p.pre = v.pre; p.post = v.mid;
+  launch_pass(ctx, p, d->n, batch);
+  // pass 2: rows
+  p.src = tmp; p.dst = dst; p.src_stride = d->n; p.dst_stride = dst_stride;
+  p.src_len = (uint32_t)d->n;
+  p.log_t = d->log_c; p.log_g = 10 - d->log_c;
+  if ((1u << p.log_g) > R) p.log_g = d->log_r;
+  p.in_p_stride = 1; p.in_g_stride = C; p.out_q_stride = R; p.out_g_stride = 1;
+  p.pre = nullptr; p.post = v.post;
+  launch_pass(ctx, p, d->n, batch);
+}
+
+}  // namespace capgpu

@@ -1,0 +1,173 @@
+/* capgpu.h -- C ABI of the B200-native PLONK proving backend for CAP (jf-cap 0.0.4).
+ *
+ * This is the drop-in boundary: the entry points a Rust `capgpu-sys` crate binds (see
+ * INTEGRATION.md) in place of the CPU routines that `PlonkKzgSnark::prove` reaches from
+ * /root/reference/src/proof/transfer.rs:181, src/proof/mint.rs:113 and
+ * src/proof/freeze.rs:151.  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Data layout (identical to ark-ff 0.3.0 / ark-ec 0.3.0 in-memory values, so Rust slices
+ * cross without conversion):
+ *   Fr / Fq element : 4 x uint64_t little-endian limbs, MONTGOMERY form (a * 2^256 mod p)
+ *   &[Fr] of len N  : contiguous N x 4 uint64_t
+ *   G1 affine       : 8 x uint64_t = x[4] || y[4] (Fq, Montgomery); all-zero == infinity
+ *                     (Rust `GroupAffine{x,y,infinity}` is repacked to this by the shim)
+ * All host buffers are owned by the caller; the library copies in/out.  Handles are opaque
+ * and freed by their *_destroy call.  Every function returns 0 on success or a negative
+ * CAPGPU_ERR_* code; `capgpu_strerror` maps it to text; the shim maps it to
+ * `PlonkError` -> `TxnApiError::FailedSnark` (src/proof/transfer.rs:187).
+ * One `capgpu_ctx` per (host thread, GPU): a ctx owns one CUDA stream and its workspace and
+ * must not be used from two threads at once; `srs` / `pk` handles are immutable after
+ * creation and may be shared by all ctxs of the same device.  There is no CPU fallback:
+ * without a CUDA device `capgpu_ctx_create` fails with CAPGPU_ERR_CUDA.
+ */
+#ifndef CAPGPU_H
+#define CAPGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CAPGPU_OK 0
+#define CAPGPU_ERR_CUDA (-1)        /* CUDA runtime error (sticky per ctx) */
+#define CAPGPU_ERR_ARG (-2)         /* invalid argument / size */
+#define CAPGPU_ERR_DEGREE (-3)      /* quotient polynomial has the wrong degree (jf-plonk WrongQuotientPolyDegree) */
+#define CAPGPU_ERR_SRS_TOO_SMALL (-4) /* commit key shorter than the polynomial (jf-plonk / KZG10 TooManyCoefficients) */
+#define CAPGPU_ERR_STATE (-5)       /* round API called out of order */
+
+#define CAPGPU_NUM_WIRES 5          /* TurboPlonk: /root/reference/src/circuit/transfer.rs:68 */
+#define CAPGPU_NUM_SELECTORS 13     /* q_lc[4], q_mul[2], q_hash[4], q_o, q_c, q_ecc */
+#define CAPGPU_NUM_BLINDERS 17      /* wires 2x5, permutation product 3, split quotient 4 */
+
+typedef struct capgpu_ctx capgpu_ctx;
+typedef struct capgpu_srs capgpu_srs;
+typedef struct capgpu_pk capgpu_pk;
+typedef struct capgpu_job capgpu_job;
+
+const char* capgpu_strerror(int code);
+/* Text of the last CUDA error seen by this ctx ("" if none). */
+const char* capgpu_last_error(const capgpu_ctx* ctx);
+
+/* ---- context ------------------------------------------------------------------------- */
+int capgpu_ctx_create(int device, capgpu_ctx** out);
+void capgpu_ctx_destroy(capgpu_ctx* ctx);
+int capgpu_ctx_sync(capgpu_ctx* ctx);
+/* Raw cudaStream_t of the ctx (for callers that time with CUDA events). */
+void* capgpu_ctx_stream(capgpu_ctx* ctx);
+
+/* ---- SRS / commit key ------------------------------------------------------------------
+ * Replaces the `powers_of_g` vector of ark-poly-commit 0.3.0 `Powers` / `UniversalParams`
+ * (built at /root/reference/src/proof/mod.rs:59-69 or loaded at :74-109).  Uploading also
+ * precomputes the window-shifted copies 2^(c*w) * P_i used by the MSM. `window_bits` = 0
+ * lets the library choose.  */
+int capgpu_srs_upload(capgpu_ctx* ctx, const uint64_t* points_xy, size_t n_points, int window_bits, capgpu_srs** out);
+/* `KZG10::setup` on the device (PlonkKzgSnark::universal_setup, src/proof/mod.rs:59-69, minus
+ * the RNG): powers_of_g[i] = tau^i * g for the caller's tau (Fr, Montgomery) and g = (1, 2).
+ * Used for synthetic SRS in tests / benches (the Aztec CRS blob is not shipped). */
+int capgpu_srs_setup(capgpu_ctx* ctx, const uint64_t* tau, size_t n_points, int window_bits, capgpu_srs** out);
+/* Copies the first n_points bases (affine, ABI layout) back to the host. */
+int capgpu_srs_export(capgpu_ctx* ctx, const capgpu_srs* srs, uint64_t* points_xy, size_t n_points);
+void capgpu_srs_destroy(capgpu_srs* srs);
+size_t capgpu_srs_size(const capgpu_srs* srs);
+
+/* ---- G1 multi-scalar multiplication ------------------------------------------------------
+ * Replaces ark-ec 0.3.0 `VariableBaseMSM::multi_scalar_mul(&powers_of_g[base_off..], scalars)`
+ * as called by `KZG10::commit`.  `batch` independent scalar vectors of `n` elements each
+ * (stride n) over the same bases; `scalars_mont` != 0: scalars are Fr Montgomery values
+ * (what a `DensePolynomial` holds), 0: canonical `BigInteger256` (what `into_repr` gives).
+ * out_xy: batch x 8 uint64_t affine results.  */
+int capgpu_msm_g1(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const uint64_t* scalars, size_t n,
+                  size_t batch, int scalars_mont, uint64_t* out_xy);
+
+/* Same, with `scalars` and `out_xy` already resident in device memory of ctx's GPU; enqueued on
+ * the ctx stream without synchronising (pair with capgpu_ctx_sync). */
+int capgpu_msm_g1_dev(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const void* d_scalars, size_t n,
+                      size_t batch, int scalars_mont, void* d_out_xy);
+
+/* ---- radix-2 NTT over Fr -----------------------------------------------------------------
+ * Replaces ark-poly 0.3.0 `Radix2EvaluationDomain::{fft, ifft, coset_fft, coset_ifft}`
+ * (natural order in and out, coset shift = Fr::multiplicative_generator() = 5, ifft includes
+ * the 1/n scaling).  `in` holds `batch` vectors of `in_len` <= 2^log_n elements (zero-padded
+ * like arkworks), `out` receives batch x 2^log_n elements; in == out is allowed when
+ * in_len == 2^log_n.  */
+int capgpu_ntt(capgpu_ctx* ctx, const uint64_t* in, size_t in_len, uint64_t* out, unsigned log_n, size_t batch,
+               int inverse, int coset);
+
+/* Device-resident variant (d_in != d_out unless in_len == 2^log_n); asynchronous on the ctx stream. */
+int capgpu_ntt_dev(capgpu_ctx* ctx, const void* d_in, size_t in_len, void* d_out, unsigned log_n, size_t batch,
+                   int inverse, int coset);
+
+/* ---- proving key --------------------------------------------------------------------------
+ * Mirrors jf-plonk 0.1.2 `ProvingKey { sigmas, selectors, commit_key, vk }` as embedded at
+ * /root/reference/src/proof/transfer.rs:60 (built by `preprocess`, :124-155).
+ * selectors: 13 x n coefficients, sigmas: 5 x n coefficients (each padded to n), k: 5 coset
+ * representatives, selector_comms / sigma_comms: the vk commitments (13 + 5 affine points).
+ * The upload caches coset-domain evaluations of all 18 polynomials on the device.  */
+int capgpu_pk_upload(capgpu_ctx* ctx, const capgpu_srs* srs, unsigned log_n, size_t num_inputs,
+                     const uint64_t* selectors, const uint64_t* sigmas, const uint64_t* k,
+                     const uint64_t* selector_comms_xy, const uint64_t* sigma_comms_xy, capgpu_pk** out);
+/* `PlonkKzgSnark::preprocess` on the device (src/proof/transfer.rs:133): takes selector and
+ * sigma EVALUATIONS over the domain (13 x n, 5 x n), interpolates, commits, builds the pk.
+ * The computed coefficient polynomials / commitments can be read back with capgpu_pk_export. */
+int capgpu_preprocess(capgpu_ctx* ctx, const capgpu_srs* srs, unsigned log_n, size_t num_inputs,
+                      const uint64_t* selector_evals, const uint64_t* sigma_evals, const uint64_t* k, capgpu_pk** out);
+int capgpu_pk_export(capgpu_ctx* ctx, const capgpu_pk* pk, uint64_t* selectors, uint64_t* sigmas,
+                     uint64_t* selector_comms_xy, uint64_t* sigma_comms_xy);
+void capgpu_pk_destroy(capgpu_pk* pk);
+
+/* ---- proof output --------------------------------------------------------------------------
+ * Mirrors jf-plonk `Proof` (embedded at /root/reference/src/transfer.rs:60): 13 G1 + 10 Fr. */
+typedef struct capgpu_proof {
+  uint64_t wires_poly_comms[5][8];
+  uint64_t prod_perm_poly_comm[8];
+  uint64_t split_quot_poly_comms[5][8];
+  uint64_t opening_proof[8];
+  uint64_t shifted_opening_proof[8];
+  uint64_t wires_evals[5][4];
+  uint64_t wire_sigma_evals[4][4];
+  uint64_t perm_next_eval[4];
+} capgpu_proof;
+
+/* ---- whole proof -----------------------------------------------------------------------------
+ * Replaces `PlonkKzgSnark::prove::<_, _, SolidityTranscript>(rng, &circuit, &pk, Some(ext_msg))`.
+ * wires: 5 x n witness values per wire column (`witness[wire_variables[i][j]]`, Montgomery);
+ * pub_inputs: the `num_inputs` public inputs (rows 0..num_inputs-1 after
+ * finalize_for_arithmetization); blinders: the 17 field elements the prover draws from its
+ * RNG, in draw order (Montgomery, exactly the limbs `Fr::rand` returns);
+ * ext_msg: `extra_transcript_init_msg` (may be NULL).  The Fiat-Shamir transcript
+ * (jf-plonk SolidityTranscript, Keccak-256) is computed on the host inside the call. */
+int capgpu_prove(capgpu_ctx* ctx, const capgpu_pk* pk, const uint64_t* wires, const uint64_t* pub_inputs,
+                 const uint64_t* blinders, const uint8_t* ext_msg, size_t ext_msg_len, capgpu_proof* out);
+
+/* ---- round-level API ---------------------------------------------------------------------------
+ * For a host that keeps its own transcript (the Rust shim calling upstream's
+ * `PlonkTranscript`): challenges come from the caller, commitments / evaluations go back.  */
+int capgpu_job_begin(capgpu_ctx* ctx, const capgpu_pk* pk, const uint64_t* wires, const uint64_t* pub_inputs, capgpu_job** out);
+int capgpu_job_round1(capgpu_job* job, const uint64_t* blinders10, uint64_t* wire_comms_xy /*5x8*/);
+int capgpu_job_round2(capgpu_job* job, const uint64_t* beta, const uint64_t* gamma, const uint64_t* blinders3, uint64_t* z_comm_xy /*8*/);
+int capgpu_job_round3(capgpu_job* job, const uint64_t* alpha, const uint64_t* blinders4, uint64_t* split_comms_xy /*5x8*/);
+int capgpu_job_round4(capgpu_job* job, const uint64_t* zeta, uint64_t* evals /*10x4: 5 wires, 4 sigmas, z(zeta*omega)*/);
+int capgpu_job_round5(capgpu_job* job, const uint64_t* v, uint64_t* opening_comms_xy /*2x8*/);
+void capgpu_job_end(capgpu_job* job);
+
+/* ---- introspection for tests / benches ---------------------------------------------------------
+ * Copies a device-side intermediate of the last proof of this ctx to the host.
+ * what: 0 wire polys (5 x (n+2)), 1 z evals (n), 2 z poly (n+3), 3 quotient evals (8n),
+ *       4 quotient poly (8n), 5 linearisation poly (n+3), 6 opening poly (n+3),
+ *       7 shifted opening poly (n+3), 8 public-input poly (n).  */
+int capgpu_debug_read(capgpu_ctx* ctx, int what, uint64_t* out, size_t max_elems, size_t* n_elems);
+/* Number of kernel launches issued through this ctx since creation. */
+uint64_t capgpu_launch_count(const capgpu_ctx* ctx);
+
+/* ---- calibration --------------------------------------------------------------------------------
+ * Measures the integer multiply-add issue rate of this GPU (the MSM / NTT roofline
+ * denominator, which MEASURED_PEAKS.json lacks): returns giga warp-lane operations / s for
+ * plain IMAD and for IMAD.WIDE.U32, and the Montgomery multiplication rate (G mul/s). */
+int capgpu_calibrate(capgpu_ctx* ctx, double* gimad_per_s, double* gimad_wide_per_s, double* gfmul_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CAPGPU_H */

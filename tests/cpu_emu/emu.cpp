@@ -1,0 +1,46 @@
+// Host emulation harness: runs the EXACT device algorithms of cap_b200/csrc/{fp,ec}.cuh on
+// the CPU (PTX carry semantics emulated) so they can be checked against the big-int oracle
+// without a GPU.  Test infrastructure only -- never linked into the product library.
+#define CAPGPU_HOST_EMU 1
+#include "../../cap_b200/csrc/fp.cuh"
+#include <string.h>
+using namespace capgpu;
+
+extern "C" {
+void emu_fr_mul(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fr x, y; memcpy(x.v, a, 32); memcpy(y.v, b, 32); Fr z = fp_mul(x, y); memcpy(r, z.v, 32); }
+void emu_fq_mul(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fq x, y; memcpy(x.v, a, 32); memcpy(y.v, b, 32); Fq z = fp_mul(x, y); memcpy(r, z.v, 32); }
+void emu_fr_add(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fr x, y; memcpy(x.v, a, 32); memcpy(y.v, b, 32); Fr z = fp_add(x, y); memcpy(r, z.v, 32); }
+void emu_fr_sub(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fr x, y; memcpy(x.v, a, 32); memcpy(y.v, b, 32); Fr z = fp_sub(x, y); memcpy(r, z.v, 32); }
+void emu_fq_add(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fq x, y; memcpy(x.v, a, 32); memcpy(y.v, b, 32); Fq z = fp_add(x, y); memcpy(r, z.v, 32); }
+void emu_fq_sub(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fq x, y; memcpy(x.v, a, 32); memcpy(y.v, b, 32); Fq z = fp_sub(x, y); memcpy(r, z.v, 32); }
+void emu_fr_neg(const uint32_t* a, uint32_t* r) { Fr x; memcpy(x.v, a, 32); Fr z = fp_neg(x); memcpy(r, z.v, 32); }
+void emu_fr_inv(const uint32_t* a, uint32_t* r) { Fr x; memcpy(x.v, a, 32); Fr z = fp_inv(x); memcpy(r, z.v, 32); }
+void emu_fq_inv(const uint32_t* a, uint32_t* r) { Fq x; memcpy(x.v, a, 32); Fq z = fp_inv(x); memcpy(r, z.v, 32); }
+void emu_fr_from_mont(const uint32_t* a, uint32_t* r) { Fr x; memcpy(x.v, a, 32); Fr z = fp_from_mont(x); memcpy(r, z.v, 32); }
+void emu_fr_to_mont(const uint32_t* a, uint32_t* r) { Fr x; memcpy(x.v, a, 32); Fr z = fp_to_mont(x); memcpy(r, z.v, 32); }
+}
+
+#include "../../cap_b200/csrc/ec.cuh"
+extern "C" {
+// points: affine 16 x u32 (x||y Montgomery, zeros = infinity)
+void emu_g1_add_mixed_chain(const uint32_t* pts, const int* negs, int n, uint32_t* out) {
+  G1XYZZ acc = G1XYZZ::inf();
+  for (int i = 0; i < n; i++) {
+    G1Affine p; memcpy(&p, pts + 16 * i, 64);
+    if (!p.is_inf()) xyzz_add_mixed(acc, p.x, p.y, negs[i] != 0);
+  }
+  G1Affine r = xyzz_to_affine(acc); memcpy(out, &r, 64);
+}
+void emu_g1_add_full(const uint32_t* pts_a, int na, const uint32_t* pts_b, int nb, uint32_t* out) {
+  G1XYZZ a = G1XYZZ::inf(), b = G1XYZZ::inf();
+  for (int i = 0; i < na; i++) { G1Affine p; memcpy(&p, pts_a + 16 * i, 64); if (!p.is_inf()) xyzz_add_mixed(a, p.x, p.y, false); }
+  for (int i = 0; i < nb; i++) { G1Affine p; memcpy(&p, pts_b + 16 * i, 64); if (!p.is_inf()) xyzz_add_mixed(b, p.x, p.y, false); }
+  xyzz_add(a, b);
+  G1Affine r = xyzz_to_affine(a); memcpy(out, &r, 64);
+}
+void emu_g1_mul_small(const uint32_t* pt, uint32_t k, uint32_t* out) {
+  G1Affine p; memcpy(&p, pt, 64);
+  G1XYZZ r = xyzz_mul_small(xyzz_from_affine(p), k);
+  G1Affine a = xyzz_to_affine(r); memcpy(out, &a, 64);
+}
+}
