@@ -67,6 +67,14 @@ struct capgpu_ctx {
   struct capgpu_job* cached_job = nullptr;  // workspace reused across capgpu_prove calls
 };
 
+struct capgpu_srs {
+  int device = 0;
+  size_t n = 0;
+  int c = 0, W = 0;
+  size_t K = 0;  // 2^(c-1) buckets
+  capgpu::G1Affine* table = nullptr;  // W x n window-shifted bases: table[w*n + i] = 2^(c*w) * P_i
+};
+
 namespace capgpu {
 
 inline void set_device(const capgpu_ctx* ctx) { CAPGPU_CUDA(cudaSetDevice(ctx->device)); }

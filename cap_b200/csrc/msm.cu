@@ -22,14 +22,6 @@
 #include "common.cuh"
 #include <string.h>
 
-struct capgpu_srs {
-  int device = 0;
-  size_t n = 0;
-  int c = 0, W = 0;
-  size_t K = 0;  // 2^(c-1) buckets
-  capgpu::G1Affine* table = nullptr;  // W x n
-};
-
 namespace capgpu {
 
 // ------------------------------------------------------------------------------------------

@@ -1,0 +1,388 @@
+// Polynomial-side kernels of the TurboPlonk prover (everything between the NTTs and MSMs):
+// blinding, permutation grand product with batch inversion, point-wise quotient evaluation on
+// the 8n coset, quotient splitting, Horner evaluation, linearisation / batching, division by
+// (X - z).  Each replaces a CPU loop of jf-plonk 0.1.2 `Prover` / jf-relation 0.1.2
+// `PlonkCircuit` behind /root/reference/src/proof/transfer.rs:181 (names cited per kernel).
+#include "poly.cuh"
+
+namespace capgpu {
+
+// ------------------------------------------------------------------------------------------
+// Prover::mask_polynomial: p(X) + (b0 + b1 X + ..)(X^n - 1); also clears the padding tail.
+// polys: rows of `stride` elements holding n coefficients; row r gets blinders[boff[r] ..].
+// ------------------------------------------------------------------------------------------
+__global__ void blind_kernel(Fr* polys, size_t stride, size_t n, int nrows, int nb, BlindArgs args) {
+  int r = blockIdx.x;
+  if (r >= nrows) return;
+  Fr* p = polys + (size_t)r * stride;
+  for (size_t t = threadIdx.x; t < stride - n; t += blockDim.x) {
+    Fr v = Fr::zero();
+    if ((int)t < nb && r < args.rows_blinded) {
+      Fr b = args.b[r * nb + t];
+      v = b;
+      p[t] = fp_sub(p[t], b);
+    }
+    p[n + t] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Permutation grand product (jf-relation compute_prod_permutation_polynomial):
+//   z_0 = 1, z_{j+1} = z_j * prod_i (w_ij + beta*k_i*omega^j + gamma) / prod_i (w_ij + beta*sigma_ij + gamma)
+// Serial with one field division per row in the reference; here: per-row numerator and
+// denominator (gp_terms), chunk products, one block-wide scan over <= 1024 chunk products with
+// a single inversion (gp_scan), then each chunk rebuilds its prefix numerators forward and the
+// inverse prefix denominators backward (gp_finish).  15 products per row, 1 inversion total.
+// ------------------------------------------------------------------------------------------
+__global__ void gp_terms(const Fr* __restrict__ wires, size_t wstride, const Fr* __restrict__ sig_eval, const Fr* __restrict__ omega_pows,
+                         size_t n, GpArgs a, Fr* num, Fr* den) {
+  size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  Fr bw = fp_mul(a.beta, omega_pows[j]);
+  Fr nu, de;
+#pragma unroll
+  for (int i = 0; i < 5; i++) {
+    Fr w = fp_add(wires[(size_t)i * wstride + j], a.gamma);
+    Fr id = i == 0 ? bw : fp_mul(bw, a.k[i]);
+    Fr tn = fp_add(w, id);
+    Fr td = fp_add(w, fp_mul(a.beta, sig_eval[(size_t)i * n + j]));
+    nu = i == 0 ? tn : fp_mul(nu, tn);
+    de = i == 0 ? td : fp_mul(de, td);
+  }
+  num[j] = nu;
+  den[j] = de;
+}
+
+__global__ void gp_chunk_prod(const Fr* __restrict__ num, const Fr* __restrict__ den, size_t n, size_t L, Fr* cn, Fr* cd) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t T = n / L;
+  if (t >= T) return;
+  Fr pn = num[t * L], pd = den[t * L];
+  for (size_t j = t * L + 1; j < (t + 1) * L; j++) {
+    pn = fp_mul(pn, num[j]);
+    pd = fp_mul(pd, den[j]);
+  }
+  cn[t] = pn;
+  cd[t] = pd;
+}
+
+// One block, T (<= 1024) threads.  Out: cn[t] = prod_{u<t} cn_in[u] (numerator prefix at the
+// chunk start), cd[t] = 1 / prod_{u<=t} cd_in[u] (inverse denominator prefix at the chunk end).
+__global__ void __launch_bounds__(1024) gp_scan(Fr* cn, Fr* cd, int T) {
+  extern __shared__ uint32_t gp_sm[];
+  Fr* sn = reinterpret_cast<Fr*>(gp_sm);  // T entries
+  Fr* sd = sn + T;                        // T entries
+  __shared__ Fr inv_total;
+  const int t = threadIdx.x;
+  Fr myd = Fr::one();
+  if (t < T) { sn[t] = cn[t]; myd = cd[t]; sd[t] = myd; }
+  __syncthreads();
+  // inclusive prefix product of sn, inclusive suffix product of sd (Hillis-Steele)
+  for (int o = 1; o < T; o <<= 1) {
+    Fr a, b;
+    bool ha = t < T && t >= o, hb = t < T && t + o < T;
+    if (ha) a = sn[t - o];
+    if (hb) b = sd[t + o];
+    __syncthreads();
+    if (ha) sn[t] = fp_mul(sn[t], a);
+    if (hb) sd[t] = fp_mul(sd[t], b);
+    __syncthreads();
+  }
+  if (t == 0) inv_total = fp_inv(sd[0]);
+  __syncthreads();
+  if (t < T) {
+    cn[t] = t == 0 ? Fr::one() : sn[t - 1];
+    // 1 / prod_{u<=t} d_u = inv_total * prod_{u>t} d_u
+    cd[t] = t + 1 < T ? fp_mul(inv_total, sd[t + 1]) : inv_total;
+  }
+}
+
+__global__ void gp_finish(const Fr* __restrict__ num, const Fr* __restrict__ den, size_t n, size_t L, const Fr* __restrict__ cn,
+                          const Fr* __restrict__ cd, Fr* z) {
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t T = n / L;
+  if (t >= T) return;
+  Fr pn = cn[t];
+  for (size_t j = t * L; j < (t + 1) * L; j++) {
+    z[j] = pn;  // N_j = prod_{i<j} num_i
+    pn = fp_mul(pn, num[j]);
+  }
+  Fr id = cd[t];  // 1 / D_{(t+1)L}
+  for (size_t j = (t + 1) * L; j-- > t * L;) {
+    id = fp_mul(id, den[j]);  // 1 / D_j
+    z[j] = fp_mul(z[j], id);
+  }
+}
+
+void grand_product(capgpu_ctx* ctx, const Fr* wires, size_t wstride, const Fr* sig_eval, const Fr* omega_pows, size_t n,
+                   const GpArgs& a, Fr* num, Fr* den, Fr* cn, Fr* cd, Fr* z) {
+  size_t T = n / 2 < 1024 ? n / 2 : 1024;
+  if (T < 1) T = 1;
+  size_t L = n / T;
+  gp_terms<<<ceil_div(n, 128), 128, 0, ctx->stream>>>(wires, wstride, sig_eval, omega_pows, n, a, num, den);
+  CAPGPU_LAUNCH_CHECK(ctx);
+  gp_chunk_prod<<<ceil_div(T, 128), 128, 0, ctx->stream>>>(num, den, n, L, cn, cd);
+  CAPGPU_LAUNCH_CHECK(ctx);
+  unsigned threads = (unsigned)((T + 31) / 32 * 32);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CAPGPU_CUDA(cudaFuncSetAttribute(gp_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 1024 * (int)sizeof(Fr)));
+    attr_set = true;
+  }
+  gp_scan<<<1, threads, 2 * T * sizeof(Fr), ctx->stream>>>(cn, cd, (int)T);
+  CAPGPU_LAUNCH_CHECK(ctx);
+  gp_finish<<<ceil_div(T, 128), 128, 0, ctx->stream>>>(num, den, n, L, cn, cd, z);
+  CAPGPU_LAUNCH_CHECK(ctx);
+}
+
+// ------------------------------------------------------------------------------------------
+// Quotient evaluation on the 8n coset (jf-plonk Prover::compute_quotient_polynomial's point-wise
+// closure: compute_quotient_circuit_contribution + compute_quotient_copy_constraint_contribution):
+//   t(x) = (t_circ + alpha*[z(x) prod(w_i + beta k_i x + gamma) - z(wx) prod(w_i + beta sigma_i + gamma)]) / Z_H(x)
+//          + alpha^2 (z(x) - 1) / (n (x - 1))
+// One thread per coset point; 26 coalesced 32-byte streams in, one out; ~52 field products.
+// The witness-independent factors 1/Z_H (8 values) and 1/(n(x-1)) come from pk tables.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ Fr pow5(const Fr& w) {
+  Fr w2 = fp_sqr(w);
+  return fp_mul(fp_sqr(w2), w);
+}
+
+__global__ void __launch_bounds__(128) quotient_kernel(const Fr* __restrict__ coset /*7 x m: w0..w4, pi, z*/, const Fr* __restrict__ sel /*13 x m*/,
+                                                       const Fr* __restrict__ sig /*5 x m*/, const Fr* __restrict__ xs /*m*/,
+                                                       const Fr* __restrict__ l1inv /*m*/, size_t m, QuotArgs a, Fr* out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  Fr w[5];
+#pragma unroll
+  for (int j = 0; j < 5; j++) w[j] = coset[(size_t)j * m + i];
+  // gate part
+  Fr acc = fp_add(sel[11 * m + i], coset[5 * m + i]);  // q_c + PI
+#pragma unroll
+  for (int j = 0; j < 4; j++) acc = fp_add(acc, fp_mul(sel[(size_t)j * m + i], w[j]));
+  Fr w01 = fp_mul(w[0], w[1]);
+  Fr w23 = fp_mul(w[2], w[3]);
+  acc = fp_add(acc, fp_mul(sel[4 * m + i], w01));
+  acc = fp_add(acc, fp_mul(sel[5 * m + i], w23));
+#pragma unroll
+  for (int j = 0; j < 4; j++) acc = fp_add(acc, fp_mul(sel[(size_t)(6 + j) * m + i], pow5(w[j])));
+  acc = fp_sub(acc, fp_mul(sel[10 * m + i], w[4]));
+  acc = fp_add(acc, fp_mul(sel[12 * m + i], fp_mul(fp_mul(w01, w23), w[4])));
+  // permutation part
+  Fr z = coset[6 * m + i];
+  size_t inext = i + 8;
+  if (inext >= m) inext -= m;
+  Fr zn = coset[6 * m + inext];
+  Fr bx = fp_mul(a.beta, xs[i]);
+  Fr r1 = z, r2 = zn;
+#pragma unroll
+  for (int j = 0; j < 5; j++) {
+    Fr wg = fp_add(w[j], a.gamma);
+    Fr id = j == 0 ? bx : fp_mul(bx, a.k[j]);
+    r1 = fp_mul(r1, fp_add(wg, id));
+    r2 = fp_mul(r2, fp_add(wg, fp_mul(a.beta, sig[(size_t)j * m + i])));
+  }
+  acc = fp_add(acc, fp_mul(a.alpha, fp_sub(r1, r2)));
+  acc = fp_mul(acc, a.zh_inv[i & 7]);  // device table: 1 / ((g w_m^i)^n - 1), period 8
+  Fr t2 = fp_mul(fp_mul(a.alpha2, fp_sub(z, Fr::one())), l1inv[i]);
+  out[i] = fp_add(acc, t2);
+}
+
+void quotient_evals(capgpu_ctx* ctx, const Fr* coset, const Fr* sel, const Fr* sig, const Fr* xs, const Fr* l1inv, size_t m,
+                    const QuotArgs& a, Fr* out) {
+  quotient_kernel<<<ceil_div(m, 128), 128, 0, ctx->stream>>>(coset, sel, sig, xs, l1inv, m, a, out);
+  CAPGPU_LAUNCH_CHECK(ctx);
+}
+
+// pk tables: xs[i] = g * w_m^i, l1inv[i] = 1 / (n * (xs[i] - 1))
+__global__ void coset_tables_kernel(const Fr* __restrict__ omega_m, size_t m, Fr gen, Fr n_mont, Fr* xs, Fr* l1inv) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  Fr x = fp_mul(gen, omega_m[i]);
+  xs[i] = x;
+  l1inv[i] = fp_inv(fp_mul(n_mont, fp_sub(x, Fr::one())));
+}
+
+void coset_tables(capgpu_ctx* ctx, const Fr* omega_m, size_t m, const Fr& gen, const Fr& n_mont, Fr* xs, Fr* l1inv) {
+  coset_tables_kernel<<<ceil_div(m, 128), 128, 0, ctx->stream>>>(omega_m, m, gen, n_mont, xs, l1inv);
+  CAPGPU_LAUNCH_CHECK(ctx);
+}
+
+// ------------------------------------------------------------------------------------------
+// Degree check of the quotient (jf-plonk split_quotient_polynomial's WrongQuotientPolyDegree)
+// and the split into 5 chunks of n+2 coefficients with the zero-knowledge maskers:
+//   t_i(X) + b_i X^(n+2) - b_{i-1}
+// flag[0] |= 1 if any coefficient above 5n+7 is non-zero, |= 2 if coefficient 5n+7 is zero.
+// ------------------------------------------------------------------------------------------
+__global__ void split_kernel(const Fr* __restrict__ t, size_t n, size_t m, Fr* split, size_t stride, BlindArgs args, uint32_t* flag) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t deg = 5 * n + 7;
+  if (i < m) {
+    Fr c = t[i];
+    if (i > deg && !c.is_zero()) atomicOr(flag, 1u);
+    if (i == deg && c.is_zero()) atomicOr(flag, 2u);
+    if (i <= deg) {
+      size_t r = i / (n + 2);
+      size_t o = i - r * (n + 2);
+      if (r > 4) { r = 4; o = i - 4 * (n + 2); }
+      if (o == 0 && r > 0) c = fp_sub(c, args.b[r - 1]);
+      split[r * stride + o] = c;
+    }
+  }
+  // tails: row r < 4 gets b_r at position n+2, zeros after; row 4 is zero from n on
+  if (i < 5 * (stride - n)) {
+    size_t r = i / (stride - n), o = n + i % (stride - n);
+    if (r < 4) {
+      if (o == n + 2) split[r * stride + o] = args.b[r];
+      else if (o > n + 2) split[r * stride + o] = Fr::zero();
+    } else {
+      split[r * stride + o] = Fr::zero();
+    }
+  }
+}
+
+void split_quotient(capgpu_ctx* ctx, const Fr* t, size_t n, size_t m, Fr* split, size_t stride, const BlindArgs& args, uint32_t* flag) {
+  CAPGPU_CUDA(cudaMemsetAsync(flag, 0, sizeof(uint32_t), ctx->stream));
+  split_kernel<<<ceil_div(m, 256), 256, 0, ctx->stream>>>(t, n, m, split, stride, args, flag);
+  CAPGPU_LAUNCH_CHECK(ctx);
+}
+
+// ------------------------------------------------------------------------------------------
+// Horner evaluation (Prover::compute_evaluations): one CTA per (polynomial, point).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) eval_kernel(EvalArgs a, Fr* out) {
+  __shared__ Fr sm[256];
+  const int b = blockIdx.x;
+  const Fr* p = a.poly[b];
+  const size_t len = a.len[b];
+  const Fr x = a.x[b];
+  const size_t chunk = (len + blockDim.x - 1) / blockDim.x;
+  const size_t start = threadIdx.x * chunk;
+  Fr acc = Fr::zero();
+  if (start < len) {
+    size_t end = start + chunk < len ? start + chunk : len;
+    acc = p[end - 1];
+    for (size_t j = end - 1; j-- > start;) acc = fp_add(fp_mul(acc, x), p[j]);
+    acc = fp_mul(acc, fp_pow_u64(x, start));
+  }
+  sm[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) sm[threadIdx.x] = fp_add(sm[threadIdx.x], sm[threadIdx.x + o]);
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[b] = sm[0];
+}
+
+void evaluate(capgpu_ctx* ctx, const EvalArgs& a, int count, Fr* out) {
+  eval_kernel<<<count, 256, 0, ctx->stream>>>(a, out);
+  CAPGPU_LAUNCH_CHECK(ctx);
+}
+
+// ------------------------------------------------------------------------------------------
+// Linearisation polynomial and the batched opening polynomial
+// (Prover::compute_{non_,}quotient_component_for_lin_poly, compute_opening_proofs):
+//   lin   = sum_s a_s q_s + cz z + cs sigma_4 + sum_i ct_i t_i
+//   batch = lin + sum_{i<5} v^(i+1) w_i + sum_{i<4} v^(6+i) sigma_i
+// ------------------------------------------------------------------------------------------
+__global__ void lin_batch_kernel(LinArgs a, Fr* lin, Fr* batch) {
+  size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= a.len) return;
+  Fr acc = fp_mul(a.polys[6 * a.pstride + j], a.cz);  // z poly (row 6), n+3 coefficients
+  if (j < a.n) {
+#pragma unroll
+    for (int s = 0; s < 13; s++) acc = fp_add(acc, fp_mul(a.sel[(size_t)s * a.n + j], a.cs_sel[s]));
+    acc = fp_add(acc, fp_mul(a.sig[4 * a.n + j], a.csig));
+  }
+#pragma unroll
+  for (int i = 0; i < 5; i++) acc = fp_add(acc, fp_mul(a.split[(size_t)i * a.pstride + j], a.ct[i]));
+  lin[j] = acc;
+  Fr bt = acc;
+#pragma unroll
+  for (int i = 0; i < 5; i++) bt = fp_add(bt, fp_mul(a.polys[(size_t)i * a.pstride + j], a.vp[i]));
+  if (j < a.n) {
+#pragma unroll
+    for (int i = 0; i < 4; i++) bt = fp_add(bt, fp_mul(a.sig[(size_t)i * a.n + j], a.vp[5 + i]));
+  }
+  batch[j] = bt;
+}
+
+void lin_batch(capgpu_ctx* ctx, const LinArgs& a, Fr* lin, Fr* batch) {
+  lin_batch_kernel<<<ceil_div(a.len, 128), 128, 0, ctx->stream>>>(a, lin, batch);
+  CAPGPU_LAUNCH_CHECK(ctx);
+}
+
+// ------------------------------------------------------------------------------------------
+// Division by (X - point): q_{i-1} = p_i + point * q_i (the reference uses DensePolynomial
+// long division).  One CTA per polynomial: chunk-local Horner sums, a weighted suffix scan of
+// the chunk sums, then each chunk replays its recurrence from its carry.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) divide_kernel(DivArgs a) {
+  extern __shared__ uint32_t dv_sm[];
+  Fr* sh = reinterpret_cast<Fr*>(dv_sm);  // blockDim.x entries
+  const int b = blockIdx.x;
+  const Fr* p = a.src[b];
+  Fr* q = a.dst[b];
+  const size_t len = a.len[b];  // number of coefficients of p
+  const Fr x = a.x[b];
+  const int T = blockDim.x;
+  const size_t L = (len + T - 1) / T;
+  const size_t start = (size_t)threadIdx.x * L;
+  const size_t end = start + L < len ? start + L : len;
+  // H_t = sum_{j in chunk} p_j x^(j - start)
+  Fr h = Fr::zero();
+  if (start < len) {
+    h = p[end - 1];
+    for (size_t j = end - 1; j-- > start;) h = fp_add(fp_mul(h, x), p[j]);
+  }
+  // carry C_t = sum_{u > t} H_u * (x^L)^(u - t - 1): shift then weighted inclusive suffix scan
+  sh[threadIdx.x] = h;
+  __syncthreads();
+  Fr c = threadIdx.x + 1 < T ? sh[threadIdx.x + 1] : Fr::zero();
+  __syncthreads();
+  sh[threadIdx.x] = c;
+  __syncthreads();
+  Fr wgt = fp_pow_u64(x, L);
+  for (int o = 1; o < T; o <<= 1) {
+    Fr other = threadIdx.x + o < T ? sh[threadIdx.x + o] : Fr::zero();
+    __syncthreads();
+    c = fp_add(c, fp_mul(wgt, other));
+    sh[threadIdx.x] = c;
+    wgt = fp_sqr(wgt);
+    __syncthreads();
+  }
+  // replay: r = q_{end-1}
+  if (start < len) {
+    Fr r = c;
+    for (size_t i = end; i-- > start;) {
+      if (i < len - 1) q[i] = r;  // quotient has len-1 coefficients
+      r = fp_add(p[i], fp_mul(x, r));
+    }
+  }
+  // clear the slot above the quotient (buffers are reused with a fixed padded stride)
+  if (threadIdx.x == 0) q[len - 1] = Fr::zero();
+}
+
+void divide_linear(capgpu_ctx* ctx, const DivArgs& a, int count) {
+  divide_kernel<<<count, 1024, 1024 * sizeof(Fr), ctx->stream>>>(a);
+  CAPGPU_LAUNCH_CHECK(ctx);
+}
+
+// public-input evaluations: zeros except rows < num_inputs
+__global__ void fill_pi_kernel(Fr* dst, size_t n, const Fr* __restrict__ pub, size_t l) {
+  size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  dst[j] = j < l ? pub[j] : Fr::zero();
+}
+
+void fill_pi(capgpu_ctx* ctx, Fr* dst, size_t n, const Fr* pub, size_t l) {
+  fill_pi_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(dst, n, pub, l);
+  CAPGPU_LAUNCH_CHECK(ctx);
+}
+
+void blind(capgpu_ctx* ctx, Fr* polys, size_t stride, size_t n, int nrows, int nb, const BlindArgs& args) {
+  blind_kernel<<<nrows, 32, 0, ctx->stream>>>(polys, stride, n, nrows, nb, args);
+  CAPGPU_LAUNCH_CHECK(ctx);
+}
+
+}  // namespace capgpu
