@@ -1,0 +1,175 @@
+"""GPU parity tests for the standalone primitives, through the C ABI (capgpu_ntt, capgpu_msm_g1):
+bit-exact against the oracle at sizes it finishes in seconds, golden fixtures, and
+size-independent properties at the benchmark sizes."""
+import random
+
+import numpy as np
+import pytest
+
+from cap_b200 import _lib, device, field
+from oracle import bn254 as B
+from oracle import msm as omsm
+from oracle import ntt as ontt
+
+from conftest import TAU
+
+pytestmark = pytest.mark.gpu
+
+ORACLE_NTT = {(False, False): ontt.fft, (False, True): ontt.coset_fft, (True, False): ontt.ifft, (True, True): ontt.coset_ifft}
+
+
+def _h(xs):
+    return [int(x, 16) for x in xs]
+
+
+def _pt(p):
+    return None if p is None else (int(p[0], 16), int(p[1], 16))
+
+
+@pytest.mark.parametrize("log_n", [1, 2, 5, 9, 10, 11, 12, 13])
+def test_ntt_matches_oracle(ctx, log_n):
+    rng = random.Random(log_n)
+    n = 1 << log_n
+    for in_len in sorted({n, min(n, n // 8 + 3), 1}):
+        x = [rng.randrange(B.R) for _ in range(in_len)]
+        xm = field.fr_to_mont_array(x)
+        for (inverse, coset), fn in ORACLE_NTT.items():
+            got = field.fr_from_mont_array(ctx.ntt(xm, log_n, inverse, coset))
+            assert got == fn(x, log_n), (log_n, in_len, inverse, coset)
+
+
+def test_ntt_golden(ctx, golden):
+    for v in golden["ntt"]:
+        xm = field.fr_to_mont_array(_h(v["input"]))
+        for (inverse, coset), key in {(False, False): "fft", (True, False): "ifft", (False, True): "coset_fft", (True, True): "coset_ifft"}.items():
+            assert field.fr_from_mont_array(ctx.ntt(xm, v["log_n"], inverse, coset)) == _h(v[key])
+
+
+def test_ntt_edge_values_and_batch(ctx):
+    log_n = 11
+    n = 1 << log_n
+    zeros = field.fr_to_mont_array([0] * n)
+    assert field.fr_from_mont_array(ctx.ntt(zeros, log_n)) == [0] * n
+    # constant polynomial c -> all evaluations c; delta at X^1 on the coset -> 5 * omega^i
+    c = B.R - 1
+    assert field.fr_from_mont_array(ctx.ntt(field.fr_to_mont_array([c]), log_n)) == [c] * n
+    w = B.fr_root_of_unity(log_n)
+    got = field.fr_from_mont_array(ctx.ntt(field.fr_to_mont_array([0, 1]), log_n, coset=True))
+    assert got[:4] == [5 * pow(w, i, B.R) % B.R for i in range(4)]
+    rng = random.Random(3)
+    xs = [[rng.randrange(B.R) for _ in range(n)] for _ in range(3)]
+    got = ctx.ntt(np.stack([field.fr_to_mont_array(v) for v in xs]), log_n, inverse=True, coset=True)
+    for i in range(3):
+        assert field.fr_from_mont_array(got[i]) == ontt.coset_ifft(xs[i], log_n)
+
+
+@pytest.mark.parametrize("log_n", [15, 18, 20])
+def test_ntt_round_trip_and_linearity_at_bench_sizes(ctx, log_n):
+    """Size-independent properties at the prover's sizes (2^15 = n, 2^18 = 8n, 2^20 = largest)."""
+    n = 1 << log_n
+    g = np.random.default_rng(log_n)
+    a = g.integers(0, 1 << 62, size=(n, 4), dtype=np.uint64)
+    a[:, 3] &= (1 << 60) - 1  # Montgomery limbs of some value < r
+    for coset in (False, True):
+        f = ctx.ntt(a, log_n, False, coset)
+        back = ctx.ntt(f, log_n, True, coset)
+        assert np.array_equal(back, a)
+    # spot-check a few outputs against direct evaluation of the polynomial (first 64 coefficients non-zero)
+    short = a[:64]
+    coeffs = field.fr_from_mont_array(short)
+    f = field.fr_from_mont_array(ctx.ntt(short, log_n, False, True)[[0, 1, n // 2 + 3, n - 1]])
+    w = B.fr_root_of_unity(log_n)
+    for got, i in zip(f, [0, 1, n // 2 + 3, n - 1]):
+        assert got == ontt.poly_eval(coeffs, 5 * pow(w, i, B.R) % B.R)
+
+
+def test_ntt_argument_errors(ctx):
+    a = np.zeros((4, 4), dtype=np.uint64)
+    with pytest.raises(_lib.CapGpuError):
+        ctx.ntt(a, 1)  # input longer than the domain
+    with pytest.raises(_lib.CapGpuError):
+        ctx.ntt(a, 21)  # unsupported size
+
+
+@pytest.fixture(scope="module")
+def small_srs(ctx):
+    srs = device.Srs(ctx, tau_mont=field.fr_to_mont_array([TAU])[0], size=300)
+    yield srs
+    srs.close()
+
+
+def test_srs_setup_matches_oracle(ctx, small_srs, golden):
+    pts = field.g1_from_mont_array(small_srs.export(40))
+    assert pts == [_pt(p) for p in golden["msm"]["srs"]]
+    assert pts[:8] == B.srs_powers(TAU, 8)
+
+
+def test_msm_golden_and_upload_path(ctx, golden):
+    g = golden["msm"]
+    srs_pts = [_pt(p) for p in g["srs"]]
+    srs = device.Srs(ctx, points_xy=field.g1_to_mont_array(srs_pts))
+    for c in g["cases"]:
+        sc = _h(c["scalars"])
+        assert field.g1_from_mont_array(srs.msm(field.fr_to_mont_array(sc)))[0] == _pt(c["result"]), c["name"]
+        assert field.g1_from_mont_array(srs.msm(field.fr_raw_array(sc), mont=False))[0] == _pt(c["result"]), c["name"]
+    srs.close()
+
+
+@pytest.mark.parametrize("window_bits", [0, 2, 5, 11, 16])
+def test_msm_edge_cases(ctx, window_bits):
+    n = 300
+    srs = device.Srs(ctx, tau_mont=field.fr_to_mont_array([TAU])[0], size=n, window_bits=window_bits)
+    rng = random.Random(window_bits)
+    cases = {
+        "random": [rng.randrange(B.R) for _ in range(n)],
+        "zeros": [0] * n,
+        "ones": [1] * n,
+        "max": [B.R - 1] * n,
+        "small": [rng.randrange(4) for _ in range(n)],
+        "same": [0x1234567890ABCDEF] * n,
+        "half": [(B.R - 1) // 2 + rng.randrange(3) for _ in range(n)],
+    }
+    for name, sc in cases.items():
+        exp = omsm.kzg_commit_tau(sc, TAU)
+        assert field.g1_from_mont_array(srs.msm(field.fr_to_mont_array(sc)))[0] == exp, name
+    # ragged: shorter vectors, base offsets, a batch
+    sc = cases["random"]
+    pts = field.g1_from_mont_array(srs.export())
+    assert field.g1_from_mont_array(srs.msm(field.fr_to_mont_array(sc[:1])))[0] == B.g1_mul(pts[0], sc[0])
+    assert field.g1_from_mont_array(srs.msm(field.fr_to_mont_array(sc[:50]), base_off=250))[0] == omsm.msm_naive(pts[250:300], sc[:50])
+    b = np.stack([field.fr_to_mont_array(cases[k]) for k in ("random", "small", "zeros", "max", "ones")])
+    assert field.g1_from_mont_array(srs.msm(b)) == [omsm.kzg_commit_tau(cases[k], TAU) for k in ("random", "small", "zeros", "max", "ones")]
+    with pytest.raises(_lib.CapGpuError) as e:
+        srs.msm(field.fr_to_mont_array(sc[:51]), base_off=250)
+    assert e.value.code == -4  # CAPGPU_ERR_SRS_TOO_SMALL
+    srs.close()
+
+
+def test_msm_repeated_bases(ctx):
+    """Buckets that receive P, P and -P exercise the doubling / cancellation branches."""
+    P = B.g1_mul(B.G1_GEN, 99)
+    pts = [P, P, B.g1_neg(P), None] * 16
+    srs = device.Srs(ctx, points_xy=field.g1_to_mont_array(pts), window_bits=4)
+    sc = [7] * 64
+    assert field.g1_from_mont_array(srs.msm(field.fr_to_mont_array(sc)))[0] == B.g1_mul(P, 7 * 16)
+    sc = [3, 3, 6, 1] * 16
+    assert field.g1_from_mont_array(srs.msm(field.fr_to_mont_array(sc)))[0] is None
+    srs.close()
+
+
+@pytest.mark.parametrize("log_n", [15, 17])
+def test_msm_at_bench_sizes(ctx, log_n):
+    """Full-size check through an independent route: sum s_i tau^i G = p(tau) G, and linearity."""
+    n = (1 << log_n) + 3
+    srs = device.Srs(ctx, tau_mont=field.fr_to_mont_array([TAU])[0], size=n)
+    g = np.random.default_rng(log_n)
+    a = g.integers(0, 1 << 62, size=(2, n, 4), dtype=np.uint64)
+    a[..., 3] &= (1 << 60) - 1
+    res = field.g1_from_mont_array(srs.msm(a, mont=False))
+    for i in range(2):
+        sc = field.fr_from_raw_array(a[i])
+        assert res[i] == omsm.kzg_commit_tau(sc, TAU)
+    s0, s1 = field.fr_from_raw_array(a[0]), field.fr_from_raw_array(a[1])
+    ssum = field.fr_raw_array([(x + y) % B.R for x, y in zip(s0, s1)])
+    assert field.g1_from_mont_array(srs.msm(ssum, mont=False))[0] == B.g1_add(res[0], res[1])
+    srs.close()

@@ -1,0 +1,197 @@
+"""GPU parity tests for the whole prover through the C ABI (capgpu_preprocess, capgpu_prove, the
+round API): bit-exact against the oracle on small domains (every intermediate polynomial, every
+commitment and evaluation), the frozen golden proof, and acceptance by the oracle's verifier at
+the benchmark size.  Mirrors /root/reference/src/proof/transfer.rs:600-760 (prove then verify;
+wrong inputs are rejected) at the boundary this backend replaces."""
+import ctypes
+import random
+from ctypes import byref, c_void_p
+
+import numpy as np
+import pytest
+
+from cap_b200 import _lib, field, plonk, synth
+from cap_b200.device import _ptr
+from oracle import bn254 as B
+from oracle import plonk as oplonk
+from oracle.transcript import SolidityTranscript
+
+from conftest import TAU
+
+pytestmark = pytest.mark.gpu
+
+
+def _pt(p):
+    return None if p is None else (int(p[0], 16), int(p[1], 16))
+
+
+def _mont(xs):
+    return [B.to_mont(x, B.R) for x in xs]
+
+
+@pytest.mark.parametrize("log_n,nin", [(5, 3), (7, 0), (9, 27), (11, 27)])
+def test_prover_matches_oracle(ctx, log_n, nin):
+    rng = random.Random(log_n)
+    circ = synth.make_circuit(log_n, num_inputs=nin, seed=log_n)
+    n = circ.n
+    srs = plonk.PlonkKzgSnark.universal_setup(ctx, n + 2, TAU)
+    pk = plonk.PlonkKzgSnark.preprocess(ctx, srs, circ)
+    opk = oplonk.preprocess(circ, tau=TAU)
+    sel, sig, _, _ = pk.export()
+    assert [field.fr_from_mont_array(s) for s in sel] == opk["selectors"]
+    assert [field.fr_from_mont_array(s) for s in sig] == opk["sigmas"]
+    assert pk.vk["selector_comms"] == opk["vk"]["selector_comms"]
+    assert pk.vk["sigma_comms"] == opk["vk"]["sigma_comms"]
+    bl = [rng.randrange(B.R) for _ in range(17)]
+    msg = b"memo-ver-key-%d" % log_n
+    op = oplonk.prove(circ, opk, bl, tau=TAU, ext_msg=msg, keep=True)
+    gp = plonk.PlonkKzgSnark.prove(ctx, circ, pk, _mont(bl), msg)
+    d = op.pop("_debug")
+    assert plonk.debug_read(ctx, 0, 5 * (n + 2)) == [c for p in d["wire_polys"] for c in p]
+    assert plonk.debug_read(ctx, 8, n) == d["pi_poly"]
+    assert plonk.debug_read(ctx, 1, n) == d["z_evals"]
+    assert plonk.debug_read(ctx, 2, n + 3) == d["z_poly"]
+    tp = plonk.debug_read(ctx, 4, 8 * n)
+    assert tp[:5 * n + 8] == d["t_poly"] and not any(tp[5 * n + 8:])
+    exp_split = []
+    for p in d["split"]:
+        exp_split += list(p) + [0] * (n + 3 - len(p))
+    assert plonk.debug_read(ctx, 9, 5 * (n + 3)) == exp_split
+    assert plonk.debug_read(ctx, 5, n + 3) == d["lin"] + [0] * (n + 3 - len(d["lin"]))
+    assert plonk.debug_read(ctx, 6, n + 3)[:n + 2] == d["open_poly"] + [0] * (n + 2 - len(d["open_poly"]))
+    assert plonk.debug_read(ctx, 7, n + 3)[:n + 2] == d["shifted_poly"]
+    assert gp == op
+    assert oplonk.verify(opk["vk"], oplonk.public_input(circ), gp, TAU, ext_msg=msg)
+    assert not oplonk.verify(opk["vk"], oplonk.public_input(circ), gp, TAU, ext_msg=msg + b"x")
+    pk.close()
+    srs.close()
+
+
+def test_golden_proof(ctx, golden):
+    g = golden["proof_n32"]
+    circ = synth.make_circuit(g["log_n"], num_inputs=g["num_inputs"], seed=g["seed"])
+    srs = plonk.PlonkKzgSnark.universal_setup(ctx, circ.n + 2, int(g["tau"], 16))
+    pk = plonk.PlonkKzgSnark.preprocess(ctx, srs, circ)
+    assert pk.vk["selector_comms"] == [_pt(p) for p in g["vk"]["selector_comms"]]
+    assert pk.vk["sigma_comms"] == [_pt(p) for p in g["vk"]["sigma_comms"]]
+    proof = plonk.PlonkKzgSnark.prove(ctx, circ, pk, _mont([int(b, 16) for b in g["blinders"]]), g["ext_msg"].encode())
+    gp = g["proof"]
+    assert proof["wires_poly_comms"] == [_pt(p) for p in gp["wires_poly_comms"]]
+    assert proof["prod_perm_poly_comm"] == _pt(gp["prod_perm_poly_comm"])
+    assert proof["split_quot_poly_comms"] == [_pt(p) for p in gp["split_quot_poly_comms"]]
+    assert proof["opening_proof"] == _pt(gp["opening_proof"])
+    assert proof["shifted_opening_proof"] == _pt(gp["shifted_opening_proof"])
+    assert [hex(v) for v in proof["wires_evals"]] == gp["wires_evals"]
+    assert [hex(v) for v in proof["wire_sigma_evals"]] == gp["wire_sigma_evals"]
+    assert hex(proof["perm_next_eval"]) == gp["perm_next_eval"]
+    pk.close()
+    srs.close()
+
+
+def test_round_api_and_uploaded_key_reproduce_the_fused_proof(ctx):
+    """A host that keeps its own transcript (the Rust shim) drives the five rounds itself; a
+    ProvingKey uploaded in jf-plonk's coefficient form behaves like the preprocessed one."""
+    rng = random.Random(21)
+    circ = synth.make_circuit(8, num_inputs=4, seed=3)
+    n = circ.n
+    srs = plonk.PlonkKzgSnark.universal_setup(ctx, n + 2, TAU)
+    pk0 = plonk.PlonkKzgSnark.preprocess(ctx, srs, circ)
+    sel, sig, sc, gc = pk0.export()
+    pk = plonk.PlonkKzgSnark.upload_proving_key(ctx, srs, circ.log_n, circ.num_inputs, sel, sig, circ.k, sc, gc)
+    bl = _mont([rng.randrange(B.R) for _ in range(17)])
+    fused = plonk.PlonkKzgSnark.prove(ctx, circ, pk0, bl, b"ext")
+    assert plonk.PlonkKzgSnark.prove(ctx, circ, pk, bl, b"ext") == fused
+
+    lib = ctx.lib
+    wires = plonk.wire_values(circ)
+    pubv = plonk.public_input(circ)
+    pub = field.fr_to_mont_array(pubv)
+    blm = field.fr_raw_array(bl)
+    tr = SolidityTranscript()
+    tr.append_message(b"ext")
+    tr.append_vk_and_pub_input(pk.vk, pubv)
+    job = c_void_p()
+    _lib.check(lib.capgpu_job_begin(ctx.h, pk.h, _ptr(wires), _ptr(pub), byref(job)), ctx.h)
+    # out-of-order round is refused
+    tmp = np.zeros((5, 8), dtype=np.uint64)
+    assert lib.capgpu_job_round3(job, _ptr(blm), _ptr(blm), _ptr(tmp)) == -5
+    c1 = np.zeros((5, 8), dtype=np.uint64)
+    _lib.check(lib.capgpu_job_round1(job, _ptr(blm[:10].copy()), _ptr(c1)), ctx.h)
+    tr.append_commitments(field.g1_from_mont_array(c1))
+    beta, gamma = tr.get_and_append_challenge(), tr.get_and_append_challenge()
+    c2 = np.zeros((1, 8), dtype=np.uint64)
+    _lib.check(lib.capgpu_job_round2(job, _ptr(field.fr_to_mont_array([beta])), _ptr(field.fr_to_mont_array([gamma])), _ptr(blm[10:13].copy()), _ptr(c2)), ctx.h)
+    tr.append_commitments(field.g1_from_mont_array(c2))
+    alpha = tr.get_and_append_challenge()
+    c3 = np.zeros((5, 8), dtype=np.uint64)
+    _lib.check(lib.capgpu_job_round3(job, _ptr(field.fr_to_mont_array([alpha])), _ptr(blm[13:17].copy()), _ptr(c3)), ctx.h)
+    tr.append_commitments(field.g1_from_mont_array(c3))
+    zeta = tr.get_and_append_challenge()
+    ev = np.zeros((10, 4), dtype=np.uint64)
+    _lib.check(lib.capgpu_job_round4(job, _ptr(field.fr_to_mont_array([zeta])), _ptr(ev)), ctx.h)
+    evals = field.fr_from_mont_array(ev)
+    tr.append_proof_evaluations(evals[:5], evals[5:9], evals[9])
+    v = tr.get_and_append_challenge()
+    c5 = np.zeros((2, 8), dtype=np.uint64)
+    _lib.check(lib.capgpu_job_round5(job, _ptr(field.fr_to_mont_array([v])), _ptr(c5)), ctx.h)
+    lib.capgpu_job_end(job)
+    assert field.g1_from_mont_array(c1) == fused["wires_poly_comms"]
+    assert field.g1_from_mont_array(c2)[0] == fused["prod_perm_poly_comm"]
+    assert field.g1_from_mont_array(c3) == fused["split_quot_poly_comms"]
+    assert evals[:5] == fused["wires_evals"] and evals[5:9] == fused["wire_sigma_evals"] and evals[9] == fused["perm_next_eval"]
+    assert field.g1_from_mont_array(c5) == [fused["opening_proof"], fused["shifted_opening_proof"]]
+    pk.close()
+    pk0.close()
+    srs.close()
+
+
+def test_error_behaviour(ctx):
+    circ = synth.make_circuit(6, num_inputs=2, seed=1)
+    # SRS one point short of domain + 3 (src/utils/mod.rs:109-113: max_degree = domain + 2)
+    short = plonk.PlonkKzgSnark.universal_setup(ctx, circ.n + 1, TAU)
+    with pytest.raises(plonk.PlonkError):
+        plonk.PlonkKzgSnark.preprocess(ctx, short, circ)
+    short.close()
+    srs = plonk.PlonkKzgSnark.universal_setup(ctx, circ.n + 2, TAU)
+    pk = plonk.PlonkKzgSnark.preprocess(ctx, srs, circ)
+    bl = _mont(list(range(1, 18)))
+    good = plonk.PlonkKzgSnark.prove(ctx, circ, pk, bl)
+    assert oplonk.verify(pk.vk, plonk.public_input(circ), good, TAU)
+    # an unsatisfied witness makes the quotient a non-polynomial: jf-plonk reports
+    # WrongQuotientPolyDegree, the ABI returns CAPGPU_ERR_DEGREE
+    bad = synth.SynthCircuit(circ.log_n, circ.num_inputs, circ.selectors, circ.wire_variables, list(circ.witness), circ.k)
+    v = bad.wire_variables[4][circ.num_inputs + 3]
+    bad.witness[v] = (bad.witness[v] + 1) % B.R
+    with pytest.raises(plonk.PlonkError, match="degree"):
+        plonk.PlonkKzgSnark.prove(ctx, bad, pk, bl)
+    # the ctx stays usable afterwards
+    assert plonk.PlonkKzgSnark.prove(ctx, circ, pk, bl) == good
+    pk.close()
+    srs.close()
+
+
+def test_transfer_shape_proofs_are_accepted(ctx):
+    """BASELINE config 1 shape (n = 2^15, 27 public inputs): proofs for several witnesses under one
+    proving key are accepted by the oracle verifier, tampered ones rejected, proving is deterministic."""
+    log_n, nin = synth.NOTE_SHAPES["transfer_2x2"]
+    circ = synth.make_circuit(log_n, num_inputs=nin, seed=7)
+    srs = plonk.PlonkKzgSnark.universal_setup(ctx, circ.n + 2, TAU)
+    pk = plonk.PlonkKzgSnark.preprocess(ctx, srs, circ)
+    rng = random.Random(15)
+    for seed in (None, 1):
+        c = circ if seed is None else circ.with_witness(seed)
+        bl = _mont([rng.randrange(B.R) for _ in range(17)])
+        proof = plonk.PlonkKzgSnark.prove(ctx, c, pk, bl, b"note")
+        pub = plonk.public_input(c)
+        assert oplonk.verify(pk.vk, pub, proof, TAU, ext_msg=b"note")
+        assert plonk.PlonkKzgSnark.prove(ctx, c, pk, bl, b"note") == proof
+        bad = dict(proof)
+        bad["wires_evals"] = [proof["wires_evals"][1], proof["wires_evals"][0]] + proof["wires_evals"][2:]
+        assert not oplonk.verify(pk.vk, pub, bad, TAU, ext_msg=b"note")
+        assert not oplonk.verify(pk.vk, pub[:-1] + [(pub[-1] + 1) % B.R], proof, TAU, ext_msg=b"note")
+        # commitments equal p(tau) G for the polynomials left on the device
+        wp = plonk.debug_read(ctx, 0, 5 * (circ.n + 2))
+        from oracle.msm import kzg_commit_tau
+        assert kzg_commit_tau(wp[:circ.n + 2], TAU) == proof["wires_poly_comms"][0]
+    pk.close()
+    srs.close()
