@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""Headline benchmark: TransferNote-shaped TurboPlonk proofs / s on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this backend (one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithms, host cores
+
+A *step* is one pass of the proving hot path (PlonkKzgSnark::prove, /root/reference/src/proof/
+transfer.rs:181) over one batch of `--batch` independent synthetic notes per GPU (BASELINE
+config 5: batches of independent notes, one shard per GPU, no collective).  The workload is
+BASELINE config 1's shape: TransferNote 2-in/2-out -> domain n = 2^15, 27 public inputs
+(src/utils/mod.rs:151-153, src/proof/transfer.rs:443-458), random satisfying witness.
+
+`value`  : proofs / s with the witness columns already resident in HBM (capgpu_prove_dev).
+`e2e`    : the same through capgpu_prove with pinned HOST buffers -- H2D of the 5 x n wire
+           values and D2H of commitments / evaluations inside the timed region.
+`roofline`: the dominant kernel (MSM bucket accumulation) against the MEASURED integer
+           multiply-add issue rate of this GPU (north_star: "MSM as a fraction of the INT32 IMAD
+           peak"); algorithmic work = 10 field products (8M+2S XYZZ mixed add) x 136 wide MADs
+           per bucket addition; the NTT's HBM figure and the 2^17 MSM latency ride along.
+`cpu_baseline`: oracle/c (C restatement of the arkworks / jf-plonk CPU algorithms) on this
+           host's cores, a bounded sample, timed beside the GPU run (N = 1, rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TAU = 0x2B7E151628AED2A6ABF7158809CF4F3C762E7160F38B4DA56A784D9045190CFE
+METRIC = "transfer_note_proofs_per_sec"
+N_WITNESSES = 4
+F_MUL_WIDE_MADS = 136  # IMAD.WIDE.U32 per 254-bit Montgomery product on 8 x 32-bit limbs
+MADD_F_MULS = 10       # XYZZ mixed addition: 8M + 2S
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="capgpu", choices=["capgpu", "reference"])
+    ap.add_argument("--workload", default="transfer_2x2")
+    ap.add_argument("--batch", type=int, default=64, help="independent notes per GPU per step")
+    ap.add_argument("--ctxs", type=int, default=4, help="prover contexts (host thread + CUDA stream) per GPU")
+    ap.add_argument("--cpu-sample", type=int, default=2, help="proofs in the cpu_baseline sample (0 disables)")
+    ap.add_argument("--no-extras", action="store_true", help="skip roofline / MSM-latency / cpu_baseline side measurements")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------
+# workload
+# --------------------------------------------------------------------------------------------
+def build_workload(name: str):
+    from cap_b200 import field, plonk, synth
+    log_n, nin = synth.NOTE_SHAPES[name]
+    circ = synth.make_circuit(log_n, num_inputs=nin, seed=7)
+    circs = [circ] + [circ.with_witness(s) for s in range(1, N_WITNESSES)]
+    wires = [plonk.wire_values(c) for c in circs]
+    pubs = [field.fr_to_mont_array(plonk.public_input(c)) for c in circs]
+    rng = np.random.default_rng(2022)
+    bl = rng.integers(0, 1 << 62, size=(N_WITNESSES, 17, 4), dtype=np.uint64)
+    bl[..., 3] &= (1 << 60) - 1  # Montgomery limbs of values < r, as Fr::rand returns them
+    return circ, circs, wires, pubs, bl
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+            out, _ = self.proc.communicate()
+        sm, mx, reasons = [], [], set()
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+# this backend
+# --------------------------------------------------------------------------------------------
+def run_capgpu(args):
+    import torch
+    import torch.distributed as dist
+    from cap_b200 import _lib, device, field, plonk
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl capgpu needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    assert world == args.gpus or world == 1, f"launched with WORLD_SIZE={world} but --gpus {args.gpus}"
+
+    circ, circs, wires, pubs, bl = build_workload(args.workload)
+    n = circ.n
+    ctxs = [device.Context(local) for _ in range(args.ctxs)]
+    ctx0 = ctxs[0]
+    lib = ctx0.lib
+    srs = plonk.PlonkKzgSnark.universal_setup(ctx0, n + 2, TAU)
+    pk = plonk.PlonkKzgSnark.preprocess(ctx0, srs, circ)
+
+    # inputs: pinned host copies (e2e) and device-resident copies (value)
+    wires_pin = [torch.from_numpy(w.view(np.int64)).pin_memory() for w in wires]
+    wires_dev = [t.cuda(non_blocking=True) for t in wires_pin]
+    torch.cuda.synchronize()
+    ext = b"bench-ext-msg"
+    ext_buf = (ctypes.c_uint8 * len(ext)).from_buffer_copy(ext)
+    from ctypes import byref, c_void_p
+
+    def prove_one(ci: int, i: int, on_device: bool, out: _lib.Proof):
+        c = ctxs[ci]
+        w = i % N_WITNESSES
+        if on_device:
+            rc = lib.capgpu_prove_dev(c.h, pk.h, c_void_p(wires_dev[w].data_ptr()), device._ptr(pubs[w]), device._ptr(bl[w]), ext_buf, len(ext), byref(out))
+        else:
+            rc = lib.capgpu_prove(c.h, pk.h, c_void_p(wires_pin[w].data_ptr()), device._ptr(pubs[w]), device._ptr(bl[w]), ext_buf, len(ext), byref(out))
+        _lib.check(rc, c.h)
+
+    pool = ThreadPoolExecutor(max_workers=args.ctxs)
+    proofs = [_lib.Proof() for _ in range(args.ctxs)]
+
+    def worker(ci: int, on_device: bool):
+        for i in range(ci, args.batch, args.ctxs):
+            prove_one(ci, i, on_device, proofs[ci])
+
+    def step(on_device: bool):
+        futs = [pool.submit(worker, ci, on_device) for ci in range(args.ctxs)]
+        for f in futs:
+            f.result()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(on_device: bool, sample_clocks: bool):
+        for _ in range(args.warmup):
+            step(on_device)
+        sampler = ClockSampler(local) if sample_clocks else None
+        launches0 = sum(c.launch_count for c in ctxs)
+        barrier()
+        if sampler:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step(on_device)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if sampler else None
+        launches = sum(c.launch_count for c in ctxs) - launches0
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            lt = torch.tensor([launches], device="cuda", dtype=torch.int64)
+            dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+            launches = int(lt.item())
+        return ms, clocks, launches
+
+    # sanity: the proof from the device-resident path equals the host-buffer path
+    pa, pb = _lib.Proof(), _lib.Proof()
+    prove_one(0, 1, True, pa)
+    prove_one(0, 1, False, pb)
+    assert bytes(pa) == bytes(pb), "device-resident and host-buffer proofs differ"
+
+    ms_dev, clocks, launches = timed(True, True)
+    ms_e2e, _, _ = timed(False, False)
+    total = world * args.batch * args.steps
+    value = total / (ms_dev * 1e-3)
+    e2e_value = total / (ms_e2e * 1e-3)
+    h2d = args.batch * (5 * n * 32 + pubs[0].nbytes + 17 * 32 + len(ext))
+    d2h = args.batch * (13 * 64 + 10 * 32 + 4)
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "proofs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32 (254-bit Montgomery, 8 x 32-bit limbs)", "data": "synthetic",
+        "config": {
+            "workload": f"{args.workload}: TurboPlonk prove, domain n=2^{circ.log_n}, 5 wires, 13 selectors, {circ.num_inputs} public inputs, BN254",
+            "notes_per_gpu_per_step": args.batch, "prover_ctxs_per_gpu": args.ctxs, "distinct_witnesses": N_WITNESSES,
+            "parallelism": f"{world} x independent-note shards, no collective",
+            "cache": "per-proof working set (126 MB workspace + 159 MB cached pk cosets) exceeds the 126 MB L2; no flush needed",
+        },
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "proofs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+    }
+
+    if rank == 0 and not args.no_extras:
+        line.update(side_measurements(args, torch, ctxs, pk, srs, circ, wires_dev, wires, pubs, bl, prove_one, world))
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def side_measurements(args, torch, ctxs, pk, srs, circ, wires_dev, wires, pubs, bl, prove_one, world):
+    """Roofline of the dominant kernel, NTT bandwidth, 2^17 MSM latency, CPU baseline."""
+    from ctypes import byref, c_double, c_uint64, c_void_p
+    from cap_b200 import _lib, device, field
+    ctx = ctxs[0]
+    lib = ctx.lib
+    n = circ.n
+    out = {}
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    calib = ctx.calibrate()
+    imad_peak = max(calib["gimad_per_s"], calib["gimad_wide_per_s"])  # G lane-ops / s, measured here
+
+    # ---- per-kernel times of one proof, kernels alone on the GPU (profiling serialises the ctx)
+    _lib.check(lib.capgpu_profile_enable(ctx.h, 1), ctx.h)
+    reps = 3
+    p = _lib.Proof()
+    for i in range(reps):
+        prove_one(0, i, True, p)
+    prof = {}
+    for pid, name in enumerate(["msm_accumulate", "ntt", "quotient", "msm_sort", "msm_reduce", "grand_product"]):
+        ms, cnt, units = c_double(), c_uint64(), c_double()
+        lib.capgpu_profile_read(ctx.h, pid, byref(ms), byref(cnt), byref(units))
+        prof[name] = {"ms_per_proof": ms.value / reps, "launches_per_proof": cnt.value / reps, "units_per_proof": units.value / reps}
+    _lib.check(lib.capgpu_profile_enable(ctx.h, 0), ctx.h)
+    acc = prof["msm_accumulate"]
+    launches = max(acc["launches_per_proof"], 1)
+    madds_per_launch = acc["units_per_proof"] / launches
+    wide_mads = madds_per_launch * MADD_F_MULS * F_MUL_WIDE_MADS
+    sec_per_launch = acc["ms_per_proof"] / launches * 1e-3
+    achieved = wide_mads / sec_per_launch * 1e-9 if sec_per_launch > 0 else 0.0
+    out["roofline"] = {
+        "kernel": "msm_accumulate (Pippenger bucket accumulation, XYZZ mixed adds)",
+        "bound": "imad", "achieved": achieved, "peak": imad_peak, "unit": "G IMAD.WIDE lane-ops/s",
+        "frac": achieved / imad_peak if imad_peak else None, "traffic": None,
+        "peak_source": "measured in this run by capgpu_calibrate (integer multiply-add issue rate; MEASURED_PEAKS.json has no INT32 figure)",
+        "fmul_microbench_gmul_per_s": calib["gfmul_per_s"],
+        "algorithmic": f"{MADD_F_MULS} field products x {F_MUL_WIDE_MADS} wide MADs per bucket addition, {madds_per_launch:.0f} additions per launch",
+        "avg_launch_ms": acc["ms_per_proof"] / launches,
+    }
+    # NTT: achieved HBM-equivalent bandwidth (north_star: "NTT as achieved HBM GB/s against peak")
+    ntt = prof["ntt"]
+    hbm_peak = peaks.get("hbm_gbs")
+    # algorithmic bytes: each tile pass reads and writes its elements once: 2 x 32 B x elements
+    # butterflies = elements/2 * log_t per pass, so recover the byte count pass by pass below
+    out["kernel_times_ms_per_proof"] = {k: round(v["ms_per_proof"], 4) for k, v in prof.items()}
+
+    # ---- standalone sweeps (BASELINE config 4): NTT 2^18 and the 2^17-point MSM, device-resident
+    stream = torch.cuda.ExternalStream(ctx.stream)
+
+    def time_on_stream(fn, reps=10):
+        fn()
+        ctx.sync()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ts = []
+        for _ in range(reps):
+            with torch.cuda.stream(stream):
+                e0.record(stream)
+                fn()
+                e1.record(stream)
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return statistics.median(ts)
+
+    g = torch.Generator(device="cuda").manual_seed(1)
+    log_m = circ.log_n + 3
+    m = 1 << log_m
+    a = torch.randint(0, 1 << 60, (7, m, 4), dtype=torch.int64, device="cuda", generator=g)
+    b = torch.empty_like(a)
+    ntt_ms = time_on_stream(lambda: _lib.check(lib.capgpu_ntt_dev(ctx.h, c_void_p(a.data_ptr()), m, c_void_p(b.data_ptr()), log_m, 7, 0, 1), ctx.h))
+    ntt_bytes = 7 * m * 32 * 2 * 2  # two passes, each one read + one write of every element
+    out["ntt"] = {"size": f"7 x 2^{log_m} coset NTT", "ms": ntt_ms, "algorithmic_gbs": ntt_bytes / (ntt_ms * 1e-3) * 1e-9,
+                  "hbm_peak_gbs": hbm_peak, "frac_of_hbm": (ntt_bytes / (ntt_ms * 1e-3) * 1e-9 / hbm_peak) if hbm_peak else None,
+                  "gbutterflies_per_s": 7 * (m / 2) * log_m / (ntt_ms * 1e-3) * 1e-9,
+                  "frac_of_fmul_microbench": 7 * (m / 2) * log_m / (ntt_ms * 1e-3) * 1e-9 / calib["gfmul_per_s"]}
+    del a, b
+    n17 = 1 << 17
+    srs17 = device.Srs(ctx, tau_mont=field.fr_to_mont_array([TAU % field.R])[0], size=n17)
+    sc = torch.randint(0, 1 << 60, (n17, 4), dtype=torch.int64, device="cuda", generator=g)
+    res = torch.zeros(8, dtype=torch.int64, device="cuda")
+    msm_ms = time_on_stream(lambda: _lib.check(lib.capgpu_msm_g1_dev(ctx.h, srs17.h, 0, c_void_p(sc.data_ptr()), n17, 1, 0, c_void_p(res.data_ptr())), ctx.h))
+    # SURVEY 8(d) reference point: N = 2^17, c = 14, W = 19 -> 29.3 M field products = 3.98 G wide MADs
+    ref_wide = (10 * n17 * 19 + 28 * (1 << 13) * 19) * F_MUL_WIDE_MADS
+    out["msm_2p17"] = {"ms": msm_ms, "points": n17, "frac_of_imad_roofline_survey_formula": ref_wide / (msm_ms * 1e-3) * 1e-9 / imad_peak}
+    srs17.close()
+
+    # ---- CPU baseline: the C restatement of the reference's CPU algorithms on this host's cores
+    if world == 1 and args.cpu_sample > 0:
+        out["cpu_baseline"] = cpu_baseline(args, circ, pk, srs, wires, pubs, bl, args.cpu_sample)
+    return out
+
+
+def cpu_baseline(args, circ, pk, srs, wires, pubs, bl, sample: int):
+    from cap_b200 import field, plonk
+    from oracle import cpu  # checker / baseline leg only
+    threads = os.cpu_count() or 1
+    sel, sig, sc, gc = pk.export()
+    srs_xy = srs.export()
+    sig_e = np.stack([field.fr_to_mont_array(s) for s in plonk.sigma_evals(circ)])
+    k = field.fr_to_mont_array(circ.k)
+    t0 = time.perf_counter()
+    for i in range(sample):
+        w = i % N_WITNESSES
+        rc, _ = cpu.prove(circ.log_n, circ.num_inputs, sel, sig, sig_e, k, srs_xy, sc, gc, wires[w], pubs[w], bl[w], b"bench-ext-msg", nthreads=threads)
+        assert rc == 0
+    dt = time.perf_counter() - t0
+    return {"value": sample / dt, "unit": "proofs/s", "cores": threads, "kind": "port",
+            "sample": f"{sample} proofs of the same workload, {dt:.1f} s, oracle/c/plonk_cpu.c (arkworks / jf-plonk algorithms restated in C, pthreads)"}
+
+
+# --------------------------------------------------------------------------------------------
+# reference arm: the reference's CPU path (C restatement; no Rust toolchain / crates here)
+# --------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from cap_b200 import field, plonk
+    from oracle import cpu
+    threads = os.cpu_count() or 1
+    circ, circs, wires, pubs, bl = build_workload(args.workload)
+    n = circ.n
+    srs_xy = cpu.srs(field.fr_to_mont_array([TAU % field.R])[0], n + 3, threads)
+    sel_e = np.stack([field.fr_to_mont_array(s) for s in circ.selectors])
+    sig_e = np.stack([field.fr_to_mont_array(s) for s in plonk.sigma_evals(circ)])
+    sel, sig, sc, gc = cpu.preprocess(circ.log_n, sel_e, sig_e, srs_xy, nthreads=threads)
+    k = field.fr_to_mont_array(circ.k)
+
+    def step(i):
+        w = i % N_WITNESSES
+        rc, _ = cpu.prove(circ.log_n, circ.num_inputs, sel, sig, sig_e, k, srs_xy, sc, gc, wires[w], pubs[w], bl[w], b"bench-ext-msg", nthreads=threads)
+        assert rc == 0
+
+    for i in range(args.warmup):
+        step(i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(i)
+    dt = time.perf_counter() - t0
+    value = args.steps / dt
+    sample = f"1 proof per step ({args.steps} timed), all {threads} host threads, oracle/c/plonk_cpu.c"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "proofs/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u64 (254-bit Montgomery, 4 x 64-bit limbs)", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: TurboPlonk prove, domain n=2^{circ.log_n}, 5 wires, 13 selectors, {circ.num_inputs} public inputs, BN254",
+                   "note": "reference CPU algorithms (arkworks 0.3 / jf-plonk 0.1.2) restated in C: the Rust crates are not vendored and no Rust toolchain exists in this image"},
+        "cpu_baseline": {"value": value, "unit": "proofs/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }), flush=True)
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_capgpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -124,17 +124,18 @@ __global__ void calib_imad(uint32_t* out, uint32_t m, uint32_t c, int iters) {
 
 __global__ void calib_imad_wide(uint64_t* out, uint32_t m, int iters) {
   uint64_t a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+  const uint32_t b0 = m ^ threadIdx.x, b1 = b0 + 11, b2 = b0 + 22, b3 = b0 + 33;
   for (int i = 0; i < iters; i++) {
 #pragma unroll
     for (int u = 0; u < 8; u++) {
-      asm volatile("{.reg .u32 lo; cvt.u32.u64 lo, %0; mad.wide.u32 %0, lo, %1, %0;}" : "+l"(a0) : "r"(m));
-      asm volatile("{.reg .u32 lo; cvt.u32.u64 lo, %0; mad.wide.u32 %0, lo, %1, %0;}" : "+l"(a1) : "r"(m));
-      asm volatile("{.reg .u32 lo; cvt.u32.u64 lo, %0; mad.wide.u32 %0, lo, %1, %0;}" : "+l"(a2) : "r"(m));
-      asm volatile("{.reg .u32 lo; cvt.u32.u64 lo, %0; mad.wide.u32 %0, lo, %1, %0;}" : "+l"(a3) : "r"(m));
-      asm volatile("{.reg .u32 lo; cvt.u32.u64 lo, %0; mad.wide.u32 %0, lo, %1, %0;}" : "+l"(a4) : "r"(m));
-      asm volatile("{.reg .u32 lo; cvt.u32.u64 lo, %0; mad.wide.u32 %0, lo, %1, %0;}" : "+l"(a5) : "r"(m));
-      asm volatile("{.reg .u32 lo; cvt.u32.u64 lo, %0; mad.wide.u32 %0, lo, %1, %0;}" : "+l"(a6) : "r"(m));
-      asm volatile("{.reg .u32 lo; cvt.u32.u64 lo, %0; mad.wide.u32 %0, lo, %1, %0;}" : "+l"(a7) : "r"(m));
+      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a0) : "r"(b0), "r"(m));
+      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a1) : "r"(b1), "r"(m));
+      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a2) : "r"(b2), "r"(m));
+      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a3) : "r"(b3), "r"(m));
+      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a4) : "r"(b0), "r"(b1));
+      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a5) : "r"(b1), "r"(b2));
+      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a6) : "r"(b2), "r"(b3));
+      asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a7) : "r"(b3), "r"(b0));
     }
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
@@ -188,4 +189,24 @@ extern "C" int capgpu_calibrate(capgpu_ctx* ctx, double* gimad_per_s, double* gi
     cudaEventDestroy(e1);
     cudaFree(buf);
   });
+}
+
+extern "C" int capgpu_profile_enable(capgpu_ctx* ctx, int on) {
+  if (!ctx) return CAPGPU_ERR_ARG;
+  return guarded(ctx, [&] {
+    if (on && !ctx->pe0) {
+      CAPGPU_CUDA(cudaEventCreate(&ctx->pe0));
+      CAPGPU_CUDA(cudaEventCreate(&ctx->pe1));
+    }
+    for (int i = 0; i < 8; i++) { ctx->prof_ms[i] = 0; ctx->prof_units[i] = 0; ctx->prof_cnt[i] = 0; }
+    ctx->profile = on != 0;
+  });
+}
+
+extern "C" int capgpu_profile_read(const capgpu_ctx* ctx, int id, double* total_ms, uint64_t* launches, double* units) {
+  if (!ctx || id < 0 || id >= 8) return CAPGPU_ERR_ARG;
+  if (total_ms) *total_ms = ctx->prof_ms[id];
+  if (launches) *launches = ctx->prof_cnt[id];
+  if (units) *units = ctx->prof_units[id];
+  return CAPGPU_OK;
 }

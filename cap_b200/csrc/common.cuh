@@ -62,6 +62,13 @@ struct capgpu_ctx {
   capgpu::DevBuf msm_scalars, msm_digits, msm_counts, msm_entries, msm_buckets, msm_partials, msm_out;
   void* pinned = nullptr;  // small pinned staging area
   size_t pinned_bytes = 0;
+  // optional per-kernel timing (capgpu_profile_enable): CUDA events on the ctx stream around
+  // the instrumented launches, accumulated per kernel class
+  bool profile = false;
+  cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+  double prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  double prof_units[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  uint64_t prof_cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   // debug view of the last job (device pointers owned by the job workspace)
   struct capgpu_job* last_job = nullptr;
   struct capgpu_job* cached_job = nullptr;  // workspace reused across capgpu_prove calls
@@ -105,6 +112,30 @@ int guarded(capgpu_ctx* ctx, F&& f) {
 #define CAPGPU_LAUNCH_CHECK(ctx) do { (ctx)->launches++; CAPGPU_CUDA(cudaGetLastError()); } while (0)
 
 inline unsigned ceil_div(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+// Kernel classes timed by the optional profiler (ids of capgpu_profile_read).
+enum ProfId { PROF_MSM_ACCUMULATE = 0, PROF_NTT = 1, PROF_QUOTIENT = 2, PROF_MSM_SORT = 3, PROF_MSM_REDUCE = 4, PROF_GRAND_PRODUCT = 5 };
+
+// Brackets the launches issued in its scope with CUDA events on the ctx stream when profiling
+// is on (the scope then ends with an event synchronise, so profiled runs are serialised).
+struct ProfScope {
+  capgpu_ctx* ctx;
+  int id;
+  double units;
+  ProfScope(capgpu_ctx* c, int i, double u) : ctx(c), id(i), units(u) {
+    if (ctx->profile) cudaEventRecord(ctx->pe0, ctx->stream);
+  }
+  ~ProfScope() {
+    if (!ctx->profile) return;
+    cudaEventRecord(ctx->pe1, ctx->stream);
+    if (cudaEventSynchronize(ctx->pe1) != cudaSuccess) return;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->pe0, ctx->pe1) != cudaSuccess) return;
+    ctx->prof_ms[id] += ms;
+    ctx->prof_units[id] += units;
+    ctx->prof_cnt[id]++;
+  }
+};
 
 // ---- ntt.cu -----------------------------------------------------------------------------
 NttDomain* get_domain(capgpu_ctx* ctx, unsigned log_n);

@@ -276,6 +276,8 @@ void msm_device(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const F
   uint32_t* entries = ctx->msm_entries.as<uint32_t>();
   G1XYZZ* buckets = ctx->msm_buckets.as<G1XYZZ>();
 
+  {
+  ProfScope prof_sort(ctx, PROF_MSM_SORT, (double)batch * W * n);
   CAPGPU_CUDA(cudaMemsetAsync(counts, 0, batch * (K + 2) * sizeof(uint32_t), ctx->stream));
   {
     dim3 grid(ceil_div(n, 128), (unsigned)batch);
@@ -289,10 +291,14 @@ void msm_device(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const F
     msm_scatter<<<grid, 256, 0, ctx->stream>>>(digits, n, W, cursors, entries, K, srs->n, base_off);
     CAPGPU_LAUNCH_CHECK(ctx);
   }
+  }
   // lanes per bucket: aim for ~128k accumulating threads
   size_t lpb = 1;
   while (lpb < 32 && batch * K * lpb * 2 <= 131072) lpb <<= 1;
   const size_t es = (size_t)W * n;
+  {
+  // units: upper bound on mixed additions (one per non-zero digit; zero digits have probability 2^-c)
+  ProfScope prof_acc(ctx, PROF_MSM_ACCUMULATE, (double)batch * W * n);
   switch (lpb) {
     case 1: launch_accumulate<1>(ctx, srs, entries, counts, buckets, es, batch); break;
     case 2: launch_accumulate<2>(ctx, srs, entries, counts, buckets, es, batch); break;
@@ -300,6 +306,7 @@ void msm_device(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const F
     case 8: launch_accumulate<8>(ctx, srs, entries, counts, buckets, es, batch); break;
     case 16: launch_accumulate<16>(ctx, srs, entries, counts, buckets, es, batch); break;
     default: launch_accumulate<32>(ctx, srs, entries, counts, buckets, es, batch); break;
+  }
   }
   // segmented reduction
   uint32_t L = (uint32_t)(K / 256);
@@ -310,6 +317,7 @@ void msm_device(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const F
   unsigned nblocks = ceil_div(T, block);
   ctx->msm_partials.reserve(batch * nblocks * sizeof(G1XYZZ));
   G1XYZZ* partials = ctx->msm_partials.as<G1XYZZ>();
+  ProfScope prof_red(ctx, PROF_MSM_REDUCE, (double)batch * K);
   {
     dim3 grid(nblocks, (unsigned)batch);
     msm_reduce_segments<<<grid, block, 0, ctx->stream>>>(buckets, K, L, partials);

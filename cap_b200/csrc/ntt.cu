@@ -250,6 +250,7 @@ static void launch_pass(capgpu_ctx* ctx, const NttPass& p, size_t n, size_t batc
   size_t smem = (size_t)8 * G * (T + PAD) * sizeof(uint32_t);
   unsigned threads = E / 2 >= 512 ? 512 : (E / 2 < 32 ? 32 : E / 2);
   dim3 grid((unsigned)(n / E), (unsigned)batch);
+  ProfScope prof(ctx, PROF_NTT, (double)batch * (double)(n / 2) * p.log_t);  // units: butterflies
   ntt_tile_kernel<<<grid, threads, smem, ctx->stream>>>(p);
   CAPGPU_LAUNCH_CHECK(ctx);
 }

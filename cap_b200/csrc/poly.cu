@@ -119,6 +119,7 @@ void grand_product(capgpu_ctx* ctx, const Fr* wires, size_t wstride, const Fr* s
   size_t T = n / 2 < 1024 ? n / 2 : 1024;
   if (T < 1) T = 1;
   size_t L = n / T;
+  ProfScope prof(ctx, PROF_GRAND_PRODUCT, (double)n);
   gp_terms<<<ceil_div(n, 128), 128, 0, ctx->stream>>>(wires, wstride, sig_eval, omega_pows, n, a, num, den);
   CAPGPU_LAUNCH_CHECK(ctx);
   gp_chunk_prod<<<ceil_div(T, 128), 128, 0, ctx->stream>>>(num, den, n, L, cn, cd);
@@ -190,6 +191,7 @@ __global__ void __launch_bounds__(128) quotient_kernel(const Fr* __restrict__ co
 
 void quotient_evals(capgpu_ctx* ctx, const Fr* coset, const Fr* sel, const Fr* sig, const Fr* xs, const Fr* l1inv, size_t m,
                     const QuotArgs& a, Fr* out) {
+  ProfScope prof(ctx, PROF_QUOTIENT, (double)m);
   quotient_kernel<<<ceil_div(m, 128), 128, 0, ctx->stream>>>(coset, sel, sig, xs, l1inv, m, a, out);
   CAPGPU_LAUNCH_CHECK(ctx);
 }

@@ -104,11 +104,12 @@ capgpu_job* job_acquire(capgpu_ctx* ctx, const capgpu_pk* pk) {
   return job;
 }
 
-void job_begin(capgpu_job* job, const uint64_t* wires, const uint64_t* pub_inputs) {
+void job_begin(capgpu_job* job, const uint64_t* wires, const uint64_t* pub_inputs, bool wires_on_device = false) {
   capgpu_ctx* ctx = job->ctx;
   const capgpu_pk* pk = job->pk;
   const size_t n = job->n;
-  CAPGPU_CUDA(cudaMemcpyAsync(job->wires_eval, wires, 5 * n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+  CAPGPU_CUDA(cudaMemcpyAsync(job->wires_eval, wires, 5 * n * sizeof(Fr),
+                              wires_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
   if (pk->num_inputs)
     CAPGPU_CUDA(cudaMemcpyAsync(job->pub_dev, pub_inputs, pk->num_inputs * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
   fill_pi(ctx, job->wires_eval + 5 * n, n, job->pub_dev, pk->num_inputs);
@@ -434,13 +435,26 @@ extern "C" void capgpu_job_end(capgpu_job* job) {
   if (job) job->busy = false;
 }
 
+static int prove_impl(capgpu_ctx* ctx, const capgpu_pk* pk, const uint64_t* wires, bool wires_on_device, const uint64_t* pub_inputs,
+                      const uint64_t* blinders, const uint8_t* ext_msg, size_t ext_msg_len, capgpu_proof* out);
+
 extern "C" int capgpu_prove(capgpu_ctx* ctx, const capgpu_pk* pk, const uint64_t* wires, const uint64_t* pub_inputs,
                             const uint64_t* blinders, const uint8_t* ext_msg, size_t ext_msg_len, capgpu_proof* out) {
+  return prove_impl(ctx, pk, wires, false, pub_inputs, blinders, ext_msg, ext_msg_len, out);
+}
+
+extern "C" int capgpu_prove_dev(capgpu_ctx* ctx, const capgpu_pk* pk, const void* d_wires, const uint64_t* pub_inputs,
+                                const uint64_t* blinders, const uint8_t* ext_msg, size_t ext_msg_len, capgpu_proof* out) {
+  return prove_impl(ctx, pk, (const uint64_t*)d_wires, true, pub_inputs, blinders, ext_msg, ext_msg_len, out);
+}
+
+static int prove_impl(capgpu_ctx* ctx, const capgpu_pk* pk, const uint64_t* wires, bool wires_on_device, const uint64_t* pub_inputs,
+                      const uint64_t* blinders, const uint8_t* ext_msg, size_t ext_msg_len, capgpu_proof* out) {
   if (!ctx || !pk || !wires || !blinders || !out || (!pub_inputs && pk->num_inputs) || (!ext_msg && ext_msg_len)) return CAPGPU_ERR_ARG;
   return guarded(ctx, [&] {
     capgpu_job* job = job_acquire(ctx, pk);
     struct Release { capgpu_job* j; ~Release() { j->busy = false; } } release{job};
-    job_begin(job, wires, pub_inputs);
+    job_begin(job, wires, pub_inputs, wires_on_device);
     SolidityTranscript tr;
     if (ext_msg_len) tr.append_message(ext_msg, ext_msg_len);
     tr.append_message(pk->vk_bytes.data(), pk->vk_bytes.size());

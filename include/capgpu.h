@@ -141,6 +141,11 @@ typedef struct capgpu_proof {
 int capgpu_prove(capgpu_ctx* ctx, const capgpu_pk* pk, const uint64_t* wires, const uint64_t* pub_inputs,
                  const uint64_t* blinders, const uint8_t* ext_msg, size_t ext_msg_len, capgpu_proof* out);
 
+/* Same, with the 5 x n wire values already resident in device memory of ctx's GPU (the public
+ * inputs and blinders, < 2 KB, still come from the host). */
+int capgpu_prove_dev(capgpu_ctx* ctx, const capgpu_pk* pk, const void* d_wires, const uint64_t* pub_inputs,
+                     const uint64_t* blinders, const uint8_t* ext_msg, size_t ext_msg_len, capgpu_proof* out);
+
 /* ---- round-level API ---------------------------------------------------------------------------
  * For a host that keeps its own transcript (the Rust shim calling upstream's
  * `PlonkTranscript`): challenges come from the caller, commitments / evaluations go back.  */
@@ -154,12 +159,20 @@ void capgpu_job_end(capgpu_job* job);
 
 /* ---- introspection for tests / benches ---------------------------------------------------------
  * Copies a device-side intermediate of the last proof of this ctx to the host.
- * what: 0 wire polys (5 x (n+2)), 1 z evals (n), 2 z poly (n+3), 3 quotient evals (8n),
- *       4 quotient poly (8n), 5 linearisation poly (n+3), 6 opening poly (n+3),
- *       7 shifted opening poly (n+3), 8 public-input poly (n).  */
+ * what: 0 wire polys (5 x (n+2)), 1 z evals (n), 2 z poly (n+3), 4 quotient poly (8n),
+ *       5 linearisation poly (n+3), 6 opening poly (n+3), 7 shifted opening poly (n+3),
+ *       8 public-input poly (n), 9 split quotient polys (5 x (n+3)).  */
 int capgpu_debug_read(capgpu_ctx* ctx, int what, uint64_t* out, size_t max_elems, size_t* n_elems);
 /* Number of kernel launches issued through this ctx since creation. */
 uint64_t capgpu_launch_count(const capgpu_ctx* ctx);
+
+/* Per-kernel timing with CUDA events on the ctx stream (serialises the ctx while enabled;
+ * enabling resets the counters).  id: 0 MSM bucket accumulation (units = mixed additions),
+ * 1 NTT tile passes (units = butterflies), 2 quotient evaluation (units = coset points),
+ * 3 MSM recode + sort (units = digits), 4 MSM bucket reduction (units = buckets),
+ * 5 grand product (units = rows). */
+int capgpu_profile_enable(capgpu_ctx* ctx, int on);
+int capgpu_profile_read(const capgpu_ctx* ctx, int id, double* total_ms, uint64_t* launches, double* units);
 
 /* ---- calibration --------------------------------------------------------------------------------
  * Measures the integer multiply-add issue rate of this GPU (the MSM / NTT roofline
