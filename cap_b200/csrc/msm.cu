@@ -20,6 +20,7 @@
 // `batch` scalar vectors over the same bases (the 5 wire / 5 split-quotient commitments of a
 // round) share every launch (grid.y = vector index).
 #include "common.cuh"
+#include <stdlib.h>
 #include <string.h>
 
 namespace capgpu {
@@ -89,9 +90,10 @@ __global__ void msm_recode(const Fr* scalars, size_t n, size_t stride, int mont,
 }
 
 // counts[b][0..K] -> exclusive offsets in place (entry K+1 = total); cursors = copy.
-__global__ void msm_scan(uint32_t* counts, uint32_t* cursors, size_t K) {
+__global__ void msm_scan(uint32_t* counts, uint32_t* cursors, uint32_t* order, size_t K) {
   __shared__ uint32_t warp_sums[32];
   __shared__ uint32_t carry_s;
+  __shared__ uint32_t hist[256];
   uint32_t* cnt = counts + (size_t)blockIdx.x * (K + 2);
   uint32_t* cur = cursors + (size_t)blockIdx.x * (K + 2);
   const size_t total = K + 2;
@@ -124,6 +126,35 @@ __global__ void msm_scan(uint32_t* counts, uint32_t* cursors, size_t K) {
     if (threadIdx.x == blockDim.x - 1) carry_s = excl + v;
     __syncthreads();
   }
+  // Bucket schedule: ids sorted by population, fullest first (counting sort on the clamped
+  // size).  Lanes of a warp then walk buckets of (nearly) equal length and the tail of the
+  // accumulation grid is made of the emptiest buckets.
+  uint32_t* ord = order + (size_t)blockIdx.x * K;
+  for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+  __syncthreads();
+  for (size_t k = threadIdx.x; k < K; k += blockDim.x) {
+    uint32_t sz = cnt[k + 2] - cnt[k + 1];
+    atomicAdd(&hist[255u - (sz > 255u ? 255u : sz)], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    // exclusive scan of 256 bins by one warp (8 bins per lane)
+    uint32_t loc[8], sum = 0;
+    for (int j = 0; j < 8; j++) { loc[j] = hist[threadIdx.x * 8 + j]; sum += loc[j]; }
+    uint32_t x = sum;
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+      if (threadIdx.x >= o) x += y;
+    }
+    uint32_t run = x - sum;
+    for (int j = 0; j < 8; j++) { hist[threadIdx.x * 8 + j] = run; run += loc[j]; }
+  }
+  __syncthreads();
+  for (size_t k = threadIdx.x; k < K; k += blockDim.x) {
+    uint32_t sz = cnt[k + 2] - cnt[k + 1];
+    uint32_t pos = atomicAdd(&hist[255u - (sz > 255u ? 255u : sz)], 1u);
+    ord[pos] = (uint32_t)k;
+  }
 }
 
 __global__ void msm_scatter(const int32_t* digits, size_t n, int W, uint32_t* cursors, uint32_t* entries, size_t K,
@@ -154,16 +185,18 @@ __device__ __forceinline__ G1XYZZ shfl_down_xyzz(const G1XYZZ& p, int delta, int
   return r;
 }
 
-template <int LPB>
-__global__ void __launch_bounds__(128) msm_accumulate(const G1Affine* __restrict__ table, const uint32_t* __restrict__ entries,
-                                                      const uint32_t* __restrict__ offsets, G1XYZZ* buckets, size_t K,
-                                                      size_t entries_stride) {
+template <int LPB, int MINB>
+__global__ void __launch_bounds__(128, MINB) msm_accumulate(const G1Affine* __restrict__ table, const uint32_t* __restrict__ entries,
+                                                            const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ order,
+                                                            G1XYZZ* buckets, size_t K, size_t entries_stride) {
   const size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const size_t bucket = gid / LPB;
+  const size_t slot = gid / LPB;
   const uint32_t lane = (uint32_t)(gid % LPB);
   const size_t b = blockIdx.y;
   G1XYZZ acc = G1XYZZ::inf();
-  if (bucket < K) {
+  size_t bucket = 0;
+  if (slot < K) {
+    bucket = order[b * K + slot];
     const uint32_t* off = offsets + b * (K + 2);
     uint32_t start = off[bucket + 1], end = off[bucket + 2];
     const uint32_t* ent = entries + b * entries_stride;
@@ -180,7 +213,7 @@ __global__ void __launch_bounds__(128) msm_accumulate(const G1Affine* __restrict
       xyzz_add(acc, other);
     }
   }
-  if (bucket < K && lane == 0) buckets[b * K + bucket] = acc;
+  if (slot < K && lane == 0) buckets[b * K + bucket] = acc;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -246,13 +279,40 @@ __global__ void msm_finalize(const G1XYZZ* partials, uint32_t nparts, G1Affine* 
 // ------------------------------------------------------------------------------------------
 static int ceil_log2(size_t x) { int l = 0; while (((size_t)1 << l) < x) l++; return l; }
 
-template <int LPB>
-static void launch_accumulate(capgpu_ctx* ctx, const capgpu_srs* srs, const uint32_t* entries, const uint32_t* offsets,
-                              G1XYZZ* buckets, size_t entries_stride, size_t batch) {
+struct MsmTuning {
+  int acc_minb;        // resident CTAs per SM requested from the compiler for the accumulation kernel
+  int red_seg;         // buckets per thread in the segmented reduction (0 = heuristic)
+  size_t acc_threads;  // target thread count when choosing lanes per bucket
+};
+
+static const MsmTuning& msm_tuning() {
+  static MsmTuning t = [] {
+    MsmTuning x{4, 0, 131072};
+    if (const char* e = getenv("CAPGPU_ACC_MINB")) x.acc_minb = atoi(e);
+    if (const char* e = getenv("CAPGPU_RED_SEG")) x.red_seg = atoi(e);
+    if (const char* e = getenv("CAPGPU_ACC_THREADS")) x.acc_threads = (size_t)atol(e);
+    return x;
+  }();
+  return t;
+}
+
+template <int LPB, int MINB>
+static void launch_accumulate2(capgpu_ctx* ctx, const capgpu_srs* srs, const uint32_t* entries, const uint32_t* offsets,
+                               const uint32_t* order, G1XYZZ* buckets, size_t entries_stride, size_t batch) {
   size_t threads = srs->K * LPB;
   dim3 grid(ceil_div(threads, 128), (unsigned)batch);
-  msm_accumulate<LPB><<<grid, 128, 0, ctx->stream>>>(srs->table, entries, offsets, buckets, srs->K, entries_stride);
+  msm_accumulate<LPB, MINB><<<grid, 128, 0, ctx->stream>>>(srs->table, entries, offsets, order, buckets, srs->K, entries_stride);
   CAPGPU_LAUNCH_CHECK(ctx);
+}
+
+template <int LPB>
+static void launch_accumulate(capgpu_ctx* ctx, const capgpu_srs* srs, const uint32_t* entries, const uint32_t* offsets,
+                              const uint32_t* order, G1XYZZ* buckets, size_t entries_stride, size_t batch) {
+  switch (msm_tuning().acc_minb) {
+    case 5: launch_accumulate2<LPB, 5>(ctx, srs, entries, offsets, order, buckets, entries_stride, batch); break;
+    case 6: launch_accumulate2<LPB, 6>(ctx, srs, entries, offsets, order, buckets, entries_stride, batch); break;
+    default: launch_accumulate2<LPB, 4>(ctx, srs, entries, offsets, order, buckets, entries_stride, batch); break;
+  }
 }
 
 void msm_device(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const Fr* scalars, size_t n, size_t stride,
@@ -267,12 +327,13 @@ void msm_device(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const F
     return;
   }
   ctx->msm_digits.reserve(batch * W * n * sizeof(int32_t));
-  ctx->msm_counts.reserve(2 * batch * (K + 2) * sizeof(uint32_t));
+  ctx->msm_counts.reserve((2 * batch * (K + 2) + batch * K) * sizeof(uint32_t));
   ctx->msm_entries.reserve(batch * W * n * sizeof(uint32_t));
   ctx->msm_buckets.reserve(batch * K * sizeof(G1XYZZ));
   int32_t* digits = ctx->msm_digits.as<int32_t>();
   uint32_t* counts = ctx->msm_counts.as<uint32_t>();
   uint32_t* cursors = counts + batch * (K + 2);
+  uint32_t* order = cursors + batch * (K + 2);
   uint32_t* entries = ctx->msm_entries.as<uint32_t>();
   G1XYZZ* buckets = ctx->msm_buckets.as<G1XYZZ>();
 
@@ -284,7 +345,7 @@ void msm_device(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const F
     msm_recode<<<grid, 128, 0, ctx->stream>>>(scalars, n, stride, scalars_mont ? 1 : 0, c, W, digits, counts, K);
     CAPGPU_LAUNCH_CHECK(ctx);
   }
-  msm_scan<<<(unsigned)batch, 1024, 0, ctx->stream>>>(counts, cursors, K);
+  msm_scan<<<(unsigned)batch, 1024, 0, ctx->stream>>>(counts, cursors, order, K);
   CAPGPU_LAUNCH_CHECK(ctx);
   {
     dim3 grid(ceil_div(n, 256), (unsigned)W, (unsigned)batch);
@@ -294,24 +355,28 @@ void msm_device(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const F
   }
   // lanes per bucket: aim for ~128k accumulating threads
   size_t lpb = 1;
-  while (lpb < 32 && batch * K * lpb * 2 <= 131072) lpb <<= 1;
+  while (lpb < 32 && batch * K * lpb * 2 <= msm_tuning().acc_threads) lpb <<= 1;
   const size_t es = (size_t)W * n;
   {
   // units: upper bound on mixed additions (one per non-zero digit; zero digits have probability 2^-c)
   ProfScope prof_acc(ctx, PROF_MSM_ACCUMULATE, (double)batch * W * n);
   switch (lpb) {
-    case 1: launch_accumulate<1>(ctx, srs, entries, counts, buckets, es, batch); break;
-    case 2: launch_accumulate<2>(ctx, srs, entries, counts, buckets, es, batch); break;
-    case 4: launch_accumulate<4>(ctx, srs, entries, counts, buckets, es, batch); break;
-    case 8: launch_accumulate<8>(ctx, srs, entries, counts, buckets, es, batch); break;
-    case 16: launch_accumulate<16>(ctx, srs, entries, counts, buckets, es, batch); break;
-    default: launch_accumulate<32>(ctx, srs, entries, counts, buckets, es, batch); break;
+    case 1: launch_accumulate<1>(ctx, srs, entries, counts, order, buckets, es, batch); break;
+    case 2: launch_accumulate<2>(ctx, srs, entries, counts, order, buckets, es, batch); break;
+    case 4: launch_accumulate<4>(ctx, srs, entries, counts, order, buckets, es, batch); break;
+    case 8: launch_accumulate<8>(ctx, srs, entries, counts, order, buckets, es, batch); break;
+    case 16: launch_accumulate<16>(ctx, srs, entries, counts, order, buckets, es, batch); break;
+    default: launch_accumulate<32>(ctx, srs, entries, counts, order, buckets, es, batch); break;
   }
   }
   // segmented reduction
   uint32_t L = (uint32_t)(K / 256);
   if (L < 1) L = 1;
   if (L > 16) L = 16;
+  if (msm_tuning().red_seg > 0) {
+    L = (uint32_t)msm_tuning().red_seg;
+    while (L > 1 && K / L < 32) L >>= 1;
+  }
   size_t T = K / L;
   unsigned block = T >= 256 ? 256 : (T < 32 ? 32 : (unsigned)T);
   unsigned nblocks = ceil_div(T, block);

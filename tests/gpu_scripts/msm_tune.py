@@ -1,0 +1,67 @@
+"""Dev script (gpurun): device-resident MSM timings + per-kernel profile for the current tuning
+environment (CAPGPU_ACC_MINB, CAPGPU_RED_SEG, CAPGPU_ACC_THREADS, CAPGPU_WINDOW_BITS)."""
+import json
+import os
+import statistics
+import sys
+from ctypes import byref, c_double, c_uint64, c_void_p
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+import torch  # noqa: E402
+
+from cap_b200 import _lib, device, field  # noqa: E402
+from oracle import msm as omsm  # noqa: E402
+
+TAU = 0x2B7E151628AED2A6ABF7158809CF4F3C762E7160F38B4DA56A784D9045190CFE % field.R
+wb = int(os.environ.get("CAPGPU_WINDOW_BITS", "0"))
+ctx = device.Context(0)
+lib = ctx.lib
+stream = torch.cuda.ExternalStream(ctx.stream)
+g = torch.Generator(device="cuda").manual_seed(1)
+res = {"env": {k: v for k, v in os.environ.items() if k.startswith("CAPGPU_")}}
+
+
+def timeit(fn, reps=10):
+    fn()
+    ctx.sync()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ts = []
+    for _ in range(reps):
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return statistics.median(ts)
+
+
+def profile(fn):
+    lib.capgpu_profile_enable(ctx.h, 1)
+    fn()
+    ctx.sync()
+    out = {}
+    for pid, name in enumerate(["accumulate", "ntt", "quotient", "sort", "reduce", "gp"]):
+        ms, cnt, units = c_double(), c_uint64(), c_double()
+        lib.capgpu_profile_read(ctx.h, pid, byref(ms), byref(cnt), byref(units))
+        if cnt.value:
+            out[name] = round(ms.value, 4)
+    lib.capgpu_profile_enable(ctx.h, 0)
+    return out
+
+
+for log_n, batch in ((15, 5), (15, 1), (17, 1)):
+    n = (1 << log_n) + (3 if log_n == 15 else 0)
+    srs = device.Srs(ctx, tau_mont=field.fr_to_mont_array([TAU])[0], size=n, window_bits=wb)
+    sc = torch.randint(0, 1 << 60, (batch, n, 4), dtype=torch.int64, device="cuda", generator=g)
+    out = torch.zeros((batch, 8), dtype=torch.int64, device="cuda")
+    fn = lambda: _lib.check(lib.capgpu_msm_g1_dev(ctx.h, srs.h, 0, c_void_p(sc.data_ptr()), n, batch, 0, c_void_p(out.data_ptr())), ctx.h)
+    ms = timeit(fn)
+    prof = profile(fn)
+    # correctness of the first vector through p(tau) G
+    host = sc[0].cpu().numpy().view("uint64")
+    got = field.g1_from_mont_array(out[0].cpu().numpy().view("uint64"))[0]
+    ok = got == omsm.kzg_commit_tau(field.fr_from_raw_array(host), TAU)
+    res[f"msm_2^{log_n}_x{batch}"] = {"ms": round(ms, 4), "ok": ok, **prof}
+    srs.close()
+print(json.dumps(res))
