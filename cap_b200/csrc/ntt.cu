@@ -20,6 +20,7 @@
 // (136 IMAD.WIDE) plus <= 2 table products per element, against 2 * 32 B * n of HBM traffic
 // per pass; at the prover's sizes it is bound by the integer pipe, not HBM.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace capgpu {
 
@@ -244,7 +245,168 @@ __global__ void __launch_bounds__(512) ntt_tile_kernel(NttPass P) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// register-radix tile kernel (tiles of 2^7 .. 2^10 elements)
+//
+// Each thread keeps 8 elements (64 registers) and runs up to three radix-2 stages on them
+// without touching memory (a radix-8 / radix-4 / radix-2 group per phase); phases exchange
+// elements through shared memory once (limb-planar, index padded by pos/8 so every phase's
+// access pattern is bank-conflict free).  Versus one shared-memory round trip and one barrier
+// per stage this cuts LDS/STS and barriers ~3x; the butterflies themselves (one Montgomery
+// product each) are unchanged.  Same index conventions as ntt_tile_kernel.
+// ------------------------------------------------------------------------------------------
+__host__ __device__ constexpr int ntt_num_phases(int log_t) { return log_t == 10 ? 4 : 3; }
+__host__ __device__ constexpr int ntt_phase_stages(int log_t, int ph) {
+  return log_t == 10 ? (ph < 2 ? 3 : 2)
+       : log_t == 9 ? 3
+       : log_t == 8 ? (ph < 2 ? 3 : 2)
+       : /* 7 */ (ph < 1 ? 3 : 2);
+}
+__host__ __device__ constexpr int ntt_phase_start(int log_t, int ph) {
+  int s = 0;
+  for (int i = 0; i < ph; i++) s += ntt_phase_stages(log_t, i);
+  return s;
+}
+
+__device__ __forceinline__ uint32_t ntt_pad(uint32_t pos) { return pos + (pos >> 3); }
+
+// position of element `slot` of thread t in the phase starting at stage S with RR stages
+template <int LOG_T, int S, int RR>
+__device__ __forceinline__ uint32_t ntt_slot_pos(uint32_t t, int slot) {
+  constexpr int LOG_STRIDE = LOG_T - S - RR;
+  constexpr int NGPT = 8 >> RR;
+  const uint32_t u = (uint32_t)slot >> RR, i = (uint32_t)slot & ((1u << RR) - 1u);
+  const uint32_t gid = t * NGPT + u;
+  const uint32_t hi = gid >> LOG_STRIDE, lo = gid & ((1u << LOG_STRIDE) - 1u);
+  return (hi << (LOG_STRIDE + RR)) + lo + (i << LOG_STRIDE);
+}
+
+template <int LOG_T, int S, int RR>
+__device__ __forceinline__ void ntt_phase_butterflies(Fr (&x)[8], uint32_t t, const Fr* __restrict__ tw) {
+  constexpr int LOG_STRIDE = LOG_T - S - RR;
+  constexpr int NGPT = 8 >> RR;
+#pragma unroll
+  for (int u = 0; u < NGPT; u++) {
+    const uint32_t gid = t * NGPT + u;
+    const uint32_t lo = gid & ((1u << LOG_STRIDE) - 1u);
+#pragma unroll
+    for (int l = 0; l < RR; l++) {
+      constexpr int dummy = 0;
+      (void)dummy;
+      const int half = 1 << (RR - 1 - l);
+      const int log_m = LOG_STRIDE + RR - 1 - l;
+#pragma unroll
+      for (int i = 0; i < (1 << RR); i++) {
+        if (i & half) continue;
+        const int a = (u << RR) + i, b = a + half;
+        Fr va = x[a], vb = x[b];
+        x[a] = fp_add(va, vb);
+        Fr d = fp_sub(va, vb);
+        if (log_m > 0) {
+          const uint32_t k = lo + ((uint32_t)(i & (half - 1)) << LOG_STRIDE);
+          d = fp_mul(d, tw[k << (9 - log_m)]);
+        }
+        x[b] = d;
+      }
+    }
+  }
+}
+
+template <int LOG_T, int PH>
+struct NttPhaseRunner {
+  static __device__ __forceinline__ void run(Fr (&x)[8], uint32_t t, const Fr* __restrict__ tw, uint32_t* tile, uint32_t plane) {
+    constexpr int S = ntt_phase_start(LOG_T, PH);
+    constexpr int RR = ntt_phase_stages(LOG_T, PH);
+    ntt_phase_butterflies<LOG_T, S, RR>(x, t, tw);
+    if constexpr (PH + 1 < ntt_num_phases(LOG_T)) {
+      constexpr int S2 = ntt_phase_start(LOG_T, PH + 1);
+      constexpr int RR2 = ntt_phase_stages(LOG_T, PH + 1);
+#pragma unroll
+      for (int e = 0; e < 8; e++) smem_store(tile, plane, ntt_pad(ntt_slot_pos<LOG_T, S, RR>(t, e)), x[e]);
+      __syncthreads();
+#pragma unroll
+      for (int e = 0; e < 8; e++) x[e] = smem_load(tile, plane, ntt_pad(ntt_slot_pos<LOG_T, S2, RR2>(t, e)));
+      __syncthreads();
+      NttPhaseRunner<LOG_T, PH + 1>::run(x, t, tw, tile, plane);
+    }
+  }
+};
+
+template <int LOG_T>
+__global__ void __launch_bounds__(256, 2) ntt_reg_kernel(NttPass P) {
+  extern __shared__ uint32_t smem[];
+  constexpr uint32_t T = 1u << LOG_T, TPT = T / 8, TP = T + T / 8 + 8;
+  const uint32_t G = 1u << P.log_g;
+  const uint32_t plane = G * TP;
+  uint32_t g, t;
+  if (P.in_p_stride == 1) { g = threadIdx.x / TPT; t = threadIdx.x % TPT; }  // rows: lanes walk positions
+  else { g = threadIdx.x & (G - 1); t = threadIdx.x >> P.log_g; }           // columns: lanes walk adjacent columns
+  const uint32_t gcol = blockIdx.x * G + g;
+  const Fr* src = P.src + (size_t)blockIdx.y * P.src_stride;
+  Fr* dst = P.dst + (size_t)blockIdx.y * P.dst_stride;
+  uint32_t* tile = smem + g * TP;
+
+  Fr x[8];
+  constexpr int R0 = ntt_phase_stages(LOG_T, 0);
+#pragma unroll
+  for (int e = 0; e < 8; e++) {
+    const uint32_t pos = ntt_slot_pos<LOG_T, 0, R0>(t, e);
+    const uint32_t idx = pos * P.in_p_stride + gcol * P.in_g_stride;
+    if (idx < P.src_len) {
+      x[e] = src[idx];
+      if (P.pre) x[e] = fp_mul(x[e], P.pre[pos]);
+    } else {
+      x[e] = Fr::zero();
+    }
+  }
+  NttPhaseRunner<LOG_T, 0>::run(x, t, P.tw, tile, plane);
+  constexpr int LAST = ntt_num_phases(LOG_T) - 1;
+  constexpr int SL = ntt_phase_start(LOG_T, LAST), RL = ntt_phase_stages(LOG_T, LAST);
+#pragma unroll
+  for (int e = 0; e < 8; e++) {
+    const uint32_t pos = ntt_slot_pos<LOG_T, SL, RL>(t, e);
+    const uint32_t q = __brev(pos) >> (32 - LOG_T);
+    const uint32_t oidx = q * P.out_q_stride + gcol * P.out_g_stride;
+    Fr v = x[e];
+    if (P.post) v = fp_mul(v, P.post[oidx]);
+    dst[oidx] = v;
+  }
+}
+
+template <int LOG_T>
+static void launch_reg_pass(capgpu_ctx* ctx, NttPass p, size_t n, size_t batch) {
+  constexpr uint32_t T = 1u << LOG_T, TP = T + T / 8 + 8;
+  uint32_t log_g = 11 - LOG_T;  // 2048 elements, 256 threads per CTA
+  while (((size_t)T << log_g) > n) log_g--;
+  p.log_g = log_g;
+  const uint32_t G = 1u << log_g;
+  size_t smem = (size_t)8 * G * TP * sizeof(uint32_t);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CAPGPU_CUDA(cudaFuncSetAttribute(ntt_reg_kernel<LOG_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2048 / T * TP * 4));
+    attr_set = true;
+  }
+  dim3 grid((unsigned)(n / ((size_t)T * G)), (unsigned)batch);
+  ProfScope prof(ctx, PROF_NTT, (double)batch * (double)(n / 2) * LOG_T);
+  ntt_reg_kernel<LOG_T><<<grid, G * T / 8, smem, ctx->stream>>>(p);
+  CAPGPU_LAUNCH_CHECK(ctx);
+}
+
+static bool ntt_force_v1() {
+  static bool v = getenv("CAPGPU_NTT_V1") != nullptr;
+  return v;
+}
+
 static void launch_pass(capgpu_ctx* ctx, const NttPass& p, size_t n, size_t batch) {
+  if (!ntt_force_v1()) {
+    switch (p.log_t) {
+      case 7: launch_reg_pass<7>(ctx, p, n, batch); return;
+      case 8: launch_reg_pass<8>(ctx, p, n, batch); return;
+      case 9: launch_reg_pass<9>(ctx, p, n, batch); return;
+      case 10: launch_reg_pass<10>(ctx, p, n, batch); return;
+      default: break;
+    }
+  }
   uint32_t T = 1u << p.log_t, G = 1u << p.log_g, E = T * G;
   uint32_t PAD = G > 1 ? (32u / G ? 32u / G : 1u) : 0u;
   size_t smem = (size_t)8 * G * (T + PAD) * sizeof(uint32_t);

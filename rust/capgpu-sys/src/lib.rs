@@ -1,0 +1,54 @@
+//! Raw bindings to `include/capgpu.h`.  Layouts: `Fr`/`Fq` = `[u64; 4]` Montgomery limbs (the
+//! in-memory form of ark-ff 0.3 `Fp256`), G1 affine = `[u64; 8]` = x || y, all-zero = infinity.
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_int, c_uint, c_void};
+
+#[repr(C)] pub struct capgpu_ctx { _p: [u8; 0] }
+#[repr(C)] pub struct capgpu_srs { _p: [u8; 0] }
+#[repr(C)] pub struct capgpu_pk { _p: [u8; 0] }
+#[repr(C)] pub struct capgpu_job { _p: [u8; 0] }
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct capgpu_proof {
+    pub wires_poly_comms: [[u64; 8]; 5],
+    pub prod_perm_poly_comm: [u64; 8],
+    pub split_quot_poly_comms: [[u64; 8]; 5],
+    pub opening_proof: [u64; 8],
+    pub shifted_opening_proof: [u64; 8],
+    pub wires_evals: [[u64; 4]; 5],
+    pub wire_sigma_evals: [[u64; 4]; 4],
+    pub perm_next_eval: [u64; 4],
+}
+
+pub const CAPGPU_OK: c_int = 0;
+pub const CAPGPU_ERR_CUDA: c_int = -1;
+pub const CAPGPU_ERR_ARG: c_int = -2;
+pub const CAPGPU_ERR_DEGREE: c_int = -3;
+pub const CAPGPU_ERR_SRS_TOO_SMALL: c_int = -4;
+pub const CAPGPU_ERR_STATE: c_int = -5;
+
+extern "C" {
+    pub fn capgpu_strerror(code: c_int) -> *const c_char;
+    pub fn capgpu_last_error(ctx: *const capgpu_ctx) -> *const c_char;
+    pub fn capgpu_ctx_create(device: c_int, out: *mut *mut capgpu_ctx) -> c_int;
+    pub fn capgpu_ctx_destroy(ctx: *mut capgpu_ctx);
+    pub fn capgpu_ctx_sync(ctx: *mut capgpu_ctx) -> c_int;
+    pub fn capgpu_srs_upload(ctx: *mut capgpu_ctx, points_xy: *const u64, n_points: usize, window_bits: c_int, out: *mut *mut capgpu_srs) -> c_int;
+    pub fn capgpu_srs_destroy(srs: *mut capgpu_srs);
+    pub fn capgpu_msm_g1(ctx: *mut capgpu_ctx, srs: *const capgpu_srs, base_off: usize, scalars: *const u64, n: usize, batch: usize, scalars_mont: c_int, out_xy: *mut u64) -> c_int;
+    pub fn capgpu_ntt(ctx: *mut capgpu_ctx, input: *const u64, in_len: usize, out: *mut u64, log_n: c_uint, batch: usize, inverse: c_int, coset: c_int) -> c_int;
+    pub fn capgpu_pk_upload(ctx: *mut capgpu_ctx, srs: *const capgpu_srs, log_n: c_uint, num_inputs: usize, selectors: *const u64, sigmas: *const u64, k: *const u64, selector_comms_xy: *const u64, sigma_comms_xy: *const u64, out: *mut *mut capgpu_pk) -> c_int;
+    pub fn capgpu_pk_destroy(pk: *mut capgpu_pk);
+    pub fn capgpu_prove(ctx: *mut capgpu_ctx, pk: *const capgpu_pk, wires: *const u64, pub_inputs: *const u64, blinders: *const u64, ext_msg: *const u8, ext_msg_len: usize, out: *mut capgpu_proof) -> c_int;
+    pub fn capgpu_job_begin(ctx: *mut capgpu_ctx, pk: *const capgpu_pk, wires: *const u64, pub_inputs: *const u64, out: *mut *mut capgpu_job) -> c_int;
+    pub fn capgpu_job_round1(job: *mut capgpu_job, blinders10: *const u64, wire_comms_xy: *mut u64) -> c_int;
+    pub fn capgpu_job_round2(job: *mut capgpu_job, beta: *const u64, gamma: *const u64, blinders3: *const u64, z_comm_xy: *mut u64) -> c_int;
+    pub fn capgpu_job_round3(job: *mut capgpu_job, alpha: *const u64, blinders4: *const u64, split_comms_xy: *mut u64) -> c_int;
+    pub fn capgpu_job_round4(job: *mut capgpu_job, zeta: *const u64, evals: *mut u64) -> c_int;
+    pub fn capgpu_job_round5(job: *mut capgpu_job, v: *const u64, opening_comms_xy: *mut u64) -> c_int;
+    pub fn capgpu_job_end(job: *mut capgpu_job);
+}
+
+#[allow(dead_code)]
+fn _unused(_: *mut c_void) {}
