@@ -53,7 +53,7 @@ def parse_args():
     ap.add_argument("--impl", default="capgpu", choices=["capgpu", "reference"])
     ap.add_argument("--workload", default="transfer_2x2")
     ap.add_argument("--batch", type=int, default=64, help="independent notes per GPU per step")
-    ap.add_argument("--ctxs", type=int, default=4, help="prover contexts (host thread + CUDA stream) per GPU")
+    ap.add_argument("--ctxs", type=int, default=8, help="prover contexts (host thread + CUDA stream) per GPU")
     ap.add_argument("--cpu-sample", type=int, default=2, help="proofs in the cpu_baseline sample (0 disables)")
     ap.add_argument("--no-extras", action="store_true", help="skip roofline / MSM-latency / cpu_baseline side measurements")
     return ap.parse_args()
@@ -122,7 +122,7 @@ class ClockSampler:
 def run_capgpu(args):
     import torch
     import torch.distributed as dist
-    from cap_b200 import _lib, device, field, plonk
+    from cap_b200 import _lib, device, field, plonk, shard
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -193,13 +193,7 @@ def run_capgpu(args):
         ms = e0.elapsed_time(e1)
         clocks = sampler.stop() if sampler else None
         launches = sum(c.launch_count for c in ctxs) - launches0
-        if world > 1:
-            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-            lt = torch.tensor([launches], device="cuda", dtype=torch.int64)
-            dist.all_reduce(lt, op=dist.ReduceOp.SUM)
-            launches = int(lt.item())
+        ms, launches = shard.reduce_timing(ms, launches, device="cuda")  # max / sum over ranks
         return ms, clocks, launches
 
     # sanity: the proof from the device-resident path equals the host-buffer path

@@ -280,15 +280,13 @@ __global__ void msm_finalize(const G1XYZZ* partials, uint32_t nparts, G1Affine* 
 static int ceil_log2(size_t x) { int l = 0; while (((size_t)1 << l) < x) l++; return l; }
 
 struct MsmTuning {
-  int acc_minb;        // resident CTAs per SM requested from the compiler for the accumulation kernel
   int red_seg;         // buckets per thread in the segmented reduction (0 = heuristic)
   size_t acc_threads;  // target thread count when choosing lanes per bucket
 };
 
 static const MsmTuning& msm_tuning() {
   static MsmTuning t = [] {
-    MsmTuning x{4, 0, 131072};
-    if (const char* e = getenv("CAPGPU_ACC_MINB")) x.acc_minb = atoi(e);
+    MsmTuning x{0, 131072};
     if (const char* e = getenv("CAPGPU_RED_SEG")) x.red_seg = atoi(e);
     if (const char* e = getenv("CAPGPU_ACC_THREADS")) x.acc_threads = (size_t)atol(e);
     return x;
@@ -308,11 +306,7 @@ static void launch_accumulate2(capgpu_ctx* ctx, const capgpu_srs* srs, const uin
 template <int LPB>
 static void launch_accumulate(capgpu_ctx* ctx, const capgpu_srs* srs, const uint32_t* entries, const uint32_t* offsets,
                               const uint32_t* order, G1XYZZ* buckets, size_t entries_stride, size_t batch) {
-  switch (msm_tuning().acc_minb) {
-    case 5: launch_accumulate2<LPB, 5>(ctx, srs, entries, offsets, order, buckets, entries_stride, batch); break;
-    case 6: launch_accumulate2<LPB, 6>(ctx, srs, entries, offsets, order, buckets, entries_stride, batch); break;
-    default: launch_accumulate2<LPB, 4>(ctx, srs, entries, offsets, order, buckets, entries_stride, batch); break;
-  }
+  launch_accumulate2<LPB, 4>(ctx, srs, entries, offsets, order, buckets, entries_stride, batch);
 }
 
 void msm_device(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const Fr* scalars, size_t n, size_t stride,

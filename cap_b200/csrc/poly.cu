@@ -250,19 +250,26 @@ void split_quotient(capgpu_ctx* ctx, const Fr* t, size_t n, size_t m, Fr* split,
 }
 
 // ------------------------------------------------------------------------------------------
-// Horner evaluation (Prover::compute_evaluations): one CTA per (polynomial, point).
+// Horner evaluation (Prover::compute_evaluations): EVAL_SPLIT CTAs per (polynomial, point), each
+// evaluating one segment (thread-local Horner over a short chunk, scaled by x^start, CTA tree);
+// a second tiny kernel adds the segment sums.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) eval_kernel(EvalArgs a, Fr* out) {
-  __shared__ Fr sm[256];
-  const int b = blockIdx.x;
+constexpr int EVAL_SPLIT = 16;
+
+__global__ void __launch_bounds__(128) eval_kernel(EvalArgs a, Fr* partials) {
+  __shared__ Fr sm[128];
+  const int b = blockIdx.y;
   const Fr* p = a.poly[b];
   const size_t len = a.len[b];
   const Fr x = a.x[b];
-  const size_t chunk = (len + blockDim.x - 1) / blockDim.x;
-  const size_t start = threadIdx.x * chunk;
+  const size_t seg = (len + EVAL_SPLIT - 1) / EVAL_SPLIT;
+  const size_t seg_start = blockIdx.x * seg;
+  const size_t seg_end = seg_start + seg < len ? seg_start + seg : len;
+  const size_t chunk = (seg + blockDim.x - 1) / blockDim.x;
+  const size_t start = seg_start + threadIdx.x * chunk;
   Fr acc = Fr::zero();
-  if (start < len) {
-    size_t end = start + chunk < len ? start + chunk : len;
+  if (start < seg_end) {
+    size_t end = start + chunk < seg_end ? start + chunk : seg_end;
     acc = p[end - 1];
     for (size_t j = end - 1; j-- > start;) acc = fp_add(fp_mul(acc, x), p[j]);
     acc = fp_mul(acc, fp_pow_u64(x, start));
@@ -273,11 +280,21 @@ __global__ void __launch_bounds__(256) eval_kernel(EvalArgs a, Fr* out) {
     if ((int)threadIdx.x < o) sm[threadIdx.x] = fp_add(sm[threadIdx.x], sm[threadIdx.x + o]);
     __syncthreads();
   }
-  if (threadIdx.x == 0) out[b] = sm[0];
+  if (threadIdx.x == 0) partials[b * EVAL_SPLIT + blockIdx.x] = sm[0];
 }
 
-void evaluate(capgpu_ctx* ctx, const EvalArgs& a, int count, Fr* out) {
-  eval_kernel<<<count, 256, 0, ctx->stream>>>(a, out);
+__global__ void eval_sum_kernel(const Fr* __restrict__ partials, int count, Fr* out) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= count) return;
+  Fr acc = partials[b * EVAL_SPLIT];
+  for (int i = 1; i < EVAL_SPLIT; i++) acc = fp_add(acc, partials[b * EVAL_SPLIT + i]);
+  out[b] = acc;
+}
+
+void evaluate(capgpu_ctx* ctx, const EvalArgs& a, int count, Fr* out, Fr* scratch) {
+  eval_kernel<<<dim3(EVAL_SPLIT, count), 128, 0, ctx->stream>>>(a, scratch);
+  CAPGPU_LAUNCH_CHECK(ctx);
+  eval_sum_kernel<<<1, 32, 0, ctx->stream>>>(scratch, count, out);
   CAPGPU_LAUNCH_CHECK(ctx);
 }
 
@@ -315,58 +332,90 @@ void lin_batch(capgpu_ctx* ctx, const LinArgs& a, Fr* lin, Fr* batch) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Division by (X - point): q_{i-1} = p_i + point * q_i (the reference uses DensePolynomial
-// long division).  One CTA per polynomial: chunk-local Horner sums, a weighted suffix scan of
-// the chunk sums, then each chunk replays its recurrence from its carry.
+// Division by (X - x) (the reference uses DensePolynomial long division, a serial recurrence
+// q_{i-1} = p_i + x q_i).  Closed form: q_i = x^-(i+1) * sum_{j>i} p_j x^j, i.e. an ADDITIVE
+// suffix sum of a_j = p_j x^j.  Three grid-wide kernels: per-chunk sums of a_j, a suffix scan of
+// the chunk sums (additions only), and the per-chunk replay.  x^-1 comes from the host.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) divide_kernel(DivArgs a) {
-  extern __shared__ uint32_t dv_sm[];
-  Fr* sh = reinterpret_cast<Fr*>(dv_sm);  // blockDim.x entries
-  const int b = blockIdx.x;
+constexpr int DIV_CHUNK = 16;
+
+__global__ void __launch_bounds__(128) div_chunk_sums(DivArgs a, Fr* totals, size_t tmax) {
+  const int b = blockIdx.y;
+  const size_t len = a.len[b];
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t T = (len + DIV_CHUNK - 1) / DIV_CHUNK;
+  if (t >= T) return;
   const Fr* p = a.src[b];
-  Fr* q = a.dst[b];
-  const size_t len = a.len[b];  // number of coefficients of p
   const Fr x = a.x[b];
-  const int T = blockDim.x;
-  const size_t L = (len + T - 1) / T;
-  const size_t start = (size_t)threadIdx.x * L;
-  const size_t end = start + L < len ? start + L : len;
-  // H_t = sum_{j in chunk} p_j x^(j - start)
-  Fr h = Fr::zero();
-  if (start < len) {
-    h = p[end - 1];
-    for (size_t j = end - 1; j-- > start;) h = fp_add(fp_mul(h, x), p[j]);
+  const size_t start = t * DIV_CHUNK, end = start + DIV_CHUNK < len ? start + DIV_CHUNK : len;
+  Fr pw = fp_pow_u64(x, start);
+  Fr sum = Fr::zero();
+  for (size_t j = start; j < end; j++) {
+    sum = fp_add(sum, fp_mul(p[j], pw));
+    pw = fp_mul(pw, x);
   }
-  // carry C_t = sum_{u > t} H_u * (x^L)^(u - t - 1): shift then weighted inclusive suffix scan
-  sh[threadIdx.x] = h;
-  __syncthreads();
-  Fr c = threadIdx.x + 1 < T ? sh[threadIdx.x + 1] : Fr::zero();
-  __syncthreads();
-  sh[threadIdx.x] = c;
-  __syncthreads();
-  Fr wgt = fp_pow_u64(x, L);
-  for (int o = 1; o < T; o <<= 1) {
-    Fr other = threadIdx.x + o < T ? sh[threadIdx.x + o] : Fr::zero();
-    __syncthreads();
-    c = fp_add(c, fp_mul(wgt, other));
-    sh[threadIdx.x] = c;
-    wgt = fp_sqr(wgt);
-    __syncthreads();
-  }
-  // replay: r = q_{end-1}
-  if (start < len) {
-    Fr r = c;
-    for (size_t i = end; i-- > start;) {
-      if (i < len - 1) q[i] = r;  // quotient has len-1 coefficients
-      r = fp_add(p[i], fp_mul(x, r));
-    }
-  }
-  // clear the slot above the quotient (buffers are reused with a fixed padded stride)
-  if (threadIdx.x == 0) q[len - 1] = Fr::zero();
+  totals[b * tmax + t] = sum;
 }
 
-void divide_linear(capgpu_ctx* ctx, const DivArgs& a, int count) {
-  divide_kernel<<<count, 1024, 1024 * sizeof(Fr), ctx->stream>>>(a);
+// totals[t] <- sum_{u > t} totals[u]   (one CTA per polynomial)
+__global__ void __launch_bounds__(1024) div_scan(DivArgs a, Fr* totals, size_t tmax) {
+  __shared__ Fr sm[1024];
+  const int b = blockIdx.x;
+  const size_t T = (a.len[b] + DIV_CHUNK - 1) / DIV_CHUNK;
+  Fr* v = totals + b * tmax;
+  const size_t per = (T + blockDim.x - 1) / blockDim.x;
+  const size_t lo = threadIdx.x * per, hi = lo + per < T ? lo + per : T;
+  Fr local = Fr::zero();
+  for (size_t i = lo; i < hi; i++) local = fp_add(local, v[i]);
+  sm[threadIdx.x] = local;
+  __syncthreads();
+  // inclusive suffix scan of the per-thread sums
+  for (int o = 1; o < (int)blockDim.x; o <<= 1) {
+    Fr other = threadIdx.x + o < blockDim.x ? sm[threadIdx.x + o] : Fr::zero();
+    __syncthreads();
+    sm[threadIdx.x] = fp_add(sm[threadIdx.x], other);
+    __syncthreads();
+  }
+  Fr run = threadIdx.x + 1 < blockDim.x ? sm[threadIdx.x + 1] : Fr::zero();  // everything right of this thread
+  for (size_t i = hi; i-- > lo;) {
+    Fr cur = v[i];
+    v[i] = run;
+    run = fp_add(run, cur);
+  }
+}
+
+__global__ void __launch_bounds__(128) div_finish(DivArgs a, const Fr* __restrict__ carries, size_t tmax) {
+  const int b = blockIdx.y;
+  const size_t len = a.len[b];
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t T = (len + DIV_CHUNK - 1) / DIV_CHUNK;
+  if (t >= T) return;
+  const Fr* p = a.src[b];
+  Fr* q = a.dst[b];
+  const Fr x = a.x[b], xinv = a.xinv[b];
+  const size_t start = t * DIV_CHUNK, end = start + DIV_CHUNK < len ? start + DIV_CHUNK : len;
+  Fr run = carries[b * tmax + t];        // sum_{j >= end} p_j x^j
+  Fr pw = fp_pow_u64(x, end - 1);        // x^j for j = end-1
+  Fr ipw = fp_pow_u64(xinv, end);        // x^-(j+1)
+  for (size_t j = end; j-- > start;) {
+    q[j] = j + 1 < len ? fp_mul(run, ipw) : Fr::zero();  // the quotient has len-1 coefficients
+    run = fp_add(run, fp_mul(p[j], pw));
+    pw = fp_mul(pw, xinv);
+    ipw = fp_mul(ipw, x);
+  }
+}
+
+void divide_linear(capgpu_ctx* ctx, const DivArgs& a, int count, Fr* scratch, size_t tmax) {
+  size_t maxlen = 0;
+  for (int i = 0; i < count; i++) maxlen = a.len[i] > maxlen ? a.len[i] : maxlen;
+  const size_t T = (maxlen + DIV_CHUNK - 1) / DIV_CHUNK;
+  CAPGPU_REQUIRE(T <= tmax, "division scratch too small");
+  dim3 grid(ceil_div(T, 128), count);
+  div_chunk_sums<<<grid, 128, 0, ctx->stream>>>(a, scratch, tmax);
+  CAPGPU_LAUNCH_CHECK(ctx);
+  div_scan<<<count, 1024, 0, ctx->stream>>>(a, scratch, tmax);
+  CAPGPU_LAUNCH_CHECK(ctx);
+  div_finish<<<grid, 128, 0, ctx->stream>>>(a, scratch, tmax);
   CAPGPU_LAUNCH_CHECK(ctx);
 }
 

@@ -43,6 +43,7 @@ struct DivArgs {
   Fr* dst[2];
   size_t len[2];
   Fr x[2];
+  Fr xinv[2];
 };
 
 void blind(capgpu_ctx* ctx, Fr* polys, size_t stride, size_t n, int nrows, int nb, const BlindArgs& args);
@@ -53,8 +54,8 @@ void quotient_evals(capgpu_ctx* ctx, const Fr* coset, const Fr* sel, const Fr* s
                     const QuotArgs& a, Fr* out);
 void coset_tables(capgpu_ctx* ctx, const Fr* omega_m, size_t m, const Fr& gen, const Fr& n_mont, Fr* xs, Fr* l1inv);
 void split_quotient(capgpu_ctx* ctx, const Fr* t, size_t n, size_t m, Fr* split, size_t stride, const BlindArgs& args, uint32_t* flag);
-void evaluate(capgpu_ctx* ctx, const EvalArgs& a, int count, Fr* out);
+void evaluate(capgpu_ctx* ctx, const EvalArgs& a, int count, Fr* out, Fr* scratch /* 16 * count */);
 void lin_batch(capgpu_ctx* ctx, const LinArgs& a, Fr* lin, Fr* batch);
-void divide_linear(capgpu_ctx* ctx, const DivArgs& a, int count);
+void divide_linear(capgpu_ctx* ctx, const DivArgs& a, int count, Fr* scratch /* count * tmax */, size_t tmax);
 
 }  // namespace capgpu

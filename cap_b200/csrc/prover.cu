@@ -45,6 +45,8 @@ struct capgpu_job {
   Fr *wires_eval = nullptr, *polys = nullptr, *z_eval = nullptr, *coset = nullptr, *t = nullptr, *split = nullptr;
   Fr *lin = nullptr, *batch = nullptr, *open = nullptr, *shifted = nullptr;
   Fr *num = nullptr, *den = nullptr, *cn = nullptr, *cd = nullptr, *ntt_tmp = nullptr, *evals_dev = nullptr, *pub_dev = nullptr;
+  Fr *eval_scratch = nullptr, *div_scratch = nullptr;
+  size_t div_tmax = 0;
   G1Affine* comms_dev = nullptr;
   uint32_t* flag = nullptr;
   HFr beta, gamma, alpha, zeta, v;
@@ -77,7 +79,9 @@ capgpu_job* job_acquire(capgpu_ctx* ctx, const capgpu_pk* pk) {
     job->NP = pk->n + 8;
     job->num_inputs = pk->num_inputs;
     const size_t n = job->n, m = job->m, NP = job->NP;
-    size_t elems = 6 * n + 7 * NP + n + 7 * m + m + 5 * NP + 4 * NP + 2 * n + 2 * 1024 + 7 * m + 16 + align_up(pk->num_inputs + 1, 8);
+    job->div_tmax = (NP + 15) / 16 + 1;
+    size_t elems = 6 * n + 7 * NP + n + 7 * m + m + 5 * NP + 4 * NP + 2 * n + 2 * 1024 + 7 * m + 16 + 160 + 2 * job->div_tmax +
+                   align_up(pk->num_inputs + 1, 8);
     size_t bytes = elems * sizeof(Fr) + 8 * sizeof(G1Affine) + 256;
     job->buf.reserve(bytes);
     Fr* p = job->buf.as<Fr>();
@@ -93,6 +97,8 @@ capgpu_job* job_acquire(capgpu_ctx* ctx, const capgpu_pk* pk) {
     job->cn = take(1024); job->cd = take(1024);
     job->ntt_tmp = take(7 * m);
     job->evals_dev = take(16);
+    job->eval_scratch = take(160);
+    job->div_scratch = take(2 * job->div_tmax);
     job->pub_dev = take(align_up(pk->num_inputs + 1, 8));
     job->comms_dev = reinterpret_cast<G1Affine*>(p);
     job->flag = reinterpret_cast<uint32_t*>(job->comms_dev + 8);
@@ -204,7 +210,7 @@ void round4(capgpu_job* job, const uint64_t* zeta, uint64_t* evals_out) {
   for (int i = 0; i < 5; i++) { ea.poly[i] = job->polys + (size_t)i * NP; ea.len[i] = n + 2; ea.x[i] = to_dev(job->zeta); }
   for (int i = 0; i < 4; i++) { ea.poly[5 + i] = pk->sig_coef + (size_t)i * n; ea.len[5 + i] = n; ea.x[5 + i] = to_dev(job->zeta); }
   ea.poly[9] = job->polys + 6 * NP; ea.len[9] = n + 3; ea.x[9] = to_dev(zeta_w);
-  evaluate(ctx, ea, 10, job->evals_dev);
+  evaluate(ctx, ea, 10, job->evals_dev, job->eval_scratch);
   CAPGPU_CUDA(cudaMemcpyAsync(ctx->pinned, job->evals_dev, 10 * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
   CAPGPU_CUDA(cudaStreamSynchronize(ctx->stream));
   memcpy(evals_out, ctx->pinned, 10 * sizeof(Fr));
@@ -247,9 +253,10 @@ void round5(capgpu_job* job, const uint64_t* v_in, uint64_t* opening_comms) {
   for (int i = 0; i < 9; i++) { la.vp[i] = to_dev(vp); vp = vp * job->v; }
   lin_batch(ctx, la, job->lin, job->batch);
   DivArgs da;
-  da.src[0] = job->batch; da.dst[0] = job->open; da.len[0] = n + 3; da.x[0] = to_dev(zeta);
-  da.src[1] = job->polys + 6 * NP; da.dst[1] = job->shifted; da.len[1] = n + 3; da.x[1] = to_dev(zeta * host_omega(pk->log_n));
-  divide_linear(ctx, da, 2);
+  const HFr zeta_w = zeta * host_omega(pk->log_n);
+  da.src[0] = job->batch; da.dst[0] = job->open; da.len[0] = n + 3; da.x[0] = to_dev(zeta); da.xinv[0] = to_dev(zeta.inv());
+  da.src[1] = job->polys + 6 * NP; da.dst[1] = job->shifted; da.len[1] = n + 3; da.x[1] = to_dev(zeta_w); da.xinv[1] = to_dev(zeta_w.inv());
+  divide_linear(ctx, da, 2, job->div_scratch, job->div_tmax);
   // open and shifted are adjacent rows of stride NP
   msm_device(ctx, pk->srs, 0, job->open, n + 2, NP, 2, true, job->comms_dev);
   read_points(job, 2, opening_comms);

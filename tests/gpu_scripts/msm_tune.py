@@ -53,7 +53,8 @@ def profile(fn):
 for log_n, batch in ((15, 5), (15, 1), (17, 1)):
     n = (1 << log_n) + (3 if log_n == 15 else 0)
     srs = device.Srs(ctx, tau_mont=field.fr_to_mont_array([TAU])[0], size=n, window_bits=wb)
-    sc = torch.randint(0, 1 << 60, (batch, n, 4), dtype=torch.int64, device="cuda", generator=g)
+    sc = torch.randint(-(1 << 63), (1 << 63) - 1, (batch, n, 4), dtype=torch.int64, device="cuda", generator=g)
+    sc[..., 3] &= (1 << 60) - 1  # uniform 252-bit scalars
     out = torch.zeros((batch, 8), dtype=torch.int64, device="cuda")
     fn = lambda: _lib.check(lib.capgpu_msm_g1_dev(ctx.h, srs.h, 0, c_void_p(sc.data_ptr()), n, batch, 0, c_void_p(out.data_ptr())), ctx.h)
     ms = timeit(fn)
