@@ -228,7 +228,7 @@ def run_capgpu(args):
     if rank == 0 and not args.no_extras:
         line.update(side_measurements(args, torch, ctxs, pk, srs, circ, wires_dev, wires, pubs, bl, prove_one, world))
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(json.dumps(line))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -323,6 +323,17 @@ def side_measurements(args, torch, ctxs, pk, srs, circ, wires_dev, wires, pubs, 
     out["msm_2p17"] = {"ms": msm_ms, "points": n17, "frac_of_imad_roofline_survey_formula": ref_wide / (msm_ms * 1e-3) * 1e-9 / imad_peak}
     srs17.close()
 
+    # ---- single-proof latency (one context, nothing else on the GPU, low-latency MSM schedule)
+    lib.capgpu_ctx_set_latency_mode(ctx.h, 1)
+    p = _lib.Proof()
+    lat = []
+    for i in range(6):
+        t0 = time.perf_counter()
+        prove_one(0, i, False, p)
+        lat.append((time.perf_counter() - t0) * 1e3)
+    lib.capgpu_ctx_set_latency_mode(ctx.h, 0)
+    out["single_proof_latency_ms"] = statistics.median(lat[1:])
+
     # ---- CPU baseline: the C restatement of the reference's CPU algorithms on this host's cores
     if world == 1 and args.cpu_sample > 0:
         out["cpu_baseline"] = cpu_baseline(args, circ, pk, srs, wires, pubs, bl, args.cpu_sample)
@@ -378,7 +389,7 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     value = args.steps / dt
     sample = f"1 proof per step ({args.steps} timed), all {threads} host threads, oracle/c/plonk_cpu.c"
-    print(json.dumps({
+    emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "proofs/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64 (254-bit Montgomery, 4 x 64-bit limbs)", "data": "synthetic",
@@ -386,11 +397,25 @@ def run_reference(args):
                    "note": "reference CPU algorithms (arkworks 0.3 / jf-plonk 0.1.2) restated in C: the Rust crates are not vendored and no Rust toolchain exists in this image"},
         "cpu_baseline": {"value": value, "unit": "proofs/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }), flush=True)
+    }))
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: str):
+    """Writes the result line to the process's ORIGINAL stdout (see main)."""
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (line + "\n").encode())
 
 
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    # Exactly one JSON line may reach stdout: libraries print there too (NCCL's version banner),
+    # so fd 1 is pointed at stderr for the run and the result line goes to the saved descriptor.
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -60,6 +60,12 @@ extern "C" int capgpu_ctx_sync(capgpu_ctx* ctx) {
   return guarded(ctx, [&] { CAPGPU_CUDA(cudaStreamSynchronize(ctx->stream)); });
 }
 
+extern "C" int capgpu_ctx_set_latency_mode(capgpu_ctx* ctx, int on) {
+  if (!ctx) return CAPGPU_ERR_ARG;
+  ctx->latency_mode = on != 0;
+  return CAPGPU_OK;
+}
+
 extern "C" void* capgpu_ctx_stream(capgpu_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 
 extern "C" uint64_t capgpu_launch_count(const capgpu_ctx* ctx) { return ctx ? ctx->launches : 0; }

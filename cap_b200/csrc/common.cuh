@@ -64,6 +64,7 @@ struct capgpu_ctx {
   size_t pinned_bytes = 0;
   // optional per-kernel timing (capgpu_profile_enable): CUDA events on the ctx stream around
   // the instrumented launches, accumulated per kernel class
+  bool latency_mode = false;  // prover MSMs favour depth over total work (capgpu_ctx_set_latency_mode)
   bool profile = false;
   cudaEvent_t pe0 = nullptr, pe1 = nullptr;
   double prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -150,6 +151,6 @@ const Fr* domain_omega_powers(capgpu_ctx* ctx, unsigned log_n);  // omega^j, j <
 // ---- msm.cu -----------------------------------------------------------------------------
 // scalars: device, batch vectors of n Fr (stride `stride`); out: device, batch affine points.
 void msm_device(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const Fr* scalars, size_t n, size_t stride,
-                size_t batch, bool scalars_mont, G1Affine* out_dev);
+                size_t batch, bool scalars_mont, G1Affine* out_dev, bool latency = false);
 
 }  // namespace capgpu

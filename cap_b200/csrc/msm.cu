@@ -238,7 +238,7 @@ __device__ inline G1XYZZ block_reduce_xyzz(G1XYZZ v, G1XYZZ* smem /* >= 32 entri
   return v;  // valid in thread 0
 }
 
-__global__ void __launch_bounds__(256) msm_reduce_segments(const G1XYZZ* __restrict__ buckets, size_t K, uint32_t L,
+__global__ void __launch_bounds__(128) msm_reduce_segments(const G1XYZZ* __restrict__ buckets, size_t K, uint32_t L,
                                                            G1XYZZ* partials) {
   __shared__ G1XYZZ smem[32];
   const size_t T = K / L;
@@ -310,7 +310,7 @@ static void launch_accumulate(capgpu_ctx* ctx, const capgpu_srs* srs, const uint
 }
 
 void msm_device(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const Fr* scalars, size_t n, size_t stride,
-                size_t batch, bool scalars_mont, G1Affine* out_dev) {
+                size_t batch, bool scalars_mont, G1Affine* out_dev, bool latency) {
   if (batch == 0) return;
   if (base_off + n > srs->n) throw CodeError{CAPGPU_ERR_SRS_TOO_SMALL};
   CAPGPU_REQUIRE(srs->device == ctx->device, "SRS lives on another device");
@@ -349,7 +349,9 @@ void msm_device(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const F
   }
   // lanes per bucket: aim for ~128k accumulating threads
   size_t lpb = 1;
-  while (lpb < 32 && batch * K * lpb * 2 <= msm_tuning().acc_threads) lpb <<= 1;
+  // ... but never so many that a lane gets fewer than ~8 additions (the lane tree costs log2(lpb) full adds)
+  const size_t avg_entries = (size_t)W * n / K;
+  while (lpb < 32 && batch * K * lpb * 2 <= msm_tuning().acc_threads && lpb * 2 * 8 <= avg_entries) lpb <<= 1;
   const size_t es = (size_t)W * n;
   {
   // units: upper bound on mixed additions (one per non-zero digit; zero digits have probability 2^-c)
@@ -363,16 +365,19 @@ void msm_device(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const F
     default: launch_accumulate<32>(ctx, srs, entries, counts, order, buckets, es, batch); break;
   }
   }
-  // segmented reduction
-  uint32_t L = (uint32_t)(K / 256);
-  if (L < 1) L = 1;
-  if (L > 16) L = 16;
-  if (msm_tuning().red_seg > 0) {
-    L = (uint32_t)msm_tuning().red_seg;
-    while (L > 1 && K / L < 32) L >>= 1;
+  // segmented reduction: L buckets per thread.  Depth is ~2L + 36 group operations and work
+  // ~(K/L)(2L + 36), so a lone MSM (latency) wants a small L and a batch (throughput) a large
+  // one: L = 32 by default; in latency mode aim at ~8192 threads per launch, 4 <= L <= 32.
+  uint32_t L = 32;
+  if (latency) {
+    L = 4;
+    while (L < 32 && batch * K / (2 * L) >= 8192) L <<= 1;
   }
+  if (msm_tuning().red_seg > 0) L = (uint32_t)msm_tuning().red_seg;
+  while (L > 1 && K / L < 32) L >>= 1;
   size_t T = K / L;
-  unsigned block = T >= 256 ? 256 : (T < 32 ? 32 : (unsigned)T);
+  // 128-thread CTAs: one warp per SM sub-partition, and few enough CTAs that each gets its own SM
+  unsigned block = T >= 128 ? 128 : (T < 32 ? 32 : (unsigned)T);
   unsigned nblocks = ceil_div(T, block);
   ctx->msm_partials.reserve(batch * nblocks * sizeof(G1XYZZ));
   G1XYZZ* partials = ctx->msm_partials.as<G1XYZZ>();
@@ -467,7 +472,7 @@ extern "C" int capgpu_msm_g1(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base
     ctx->msm_scalars.reserve((batch * n + 1) * sizeof(Fr));
     ctx->msm_out.reserve(batch * sizeof(G1Affine));
     if (n) CAPGPU_CUDA(cudaMemcpyAsync(ctx->msm_scalars.p, scalars, batch * n * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
-    msm_device(ctx, srs, base_off, ctx->msm_scalars.as<Fr>(), n, n, batch, scalars_mont != 0, ctx->msm_out.as<G1Affine>());
+    msm_device(ctx, srs, base_off, ctx->msm_scalars.as<Fr>(), n, n, batch, scalars_mont != 0, ctx->msm_out.as<G1Affine>(), true);
     CAPGPU_CUDA(cudaMemcpyAsync(out_xy, ctx->msm_out.p, batch * sizeof(G1Affine), cudaMemcpyDeviceToHost, ctx->stream));
     CAPGPU_CUDA(cudaStreamSynchronize(ctx->stream));
   });
@@ -477,6 +482,6 @@ extern "C" int capgpu_msm_g1_dev(capgpu_ctx* ctx, const capgpu_srs* srs, size_t 
                                  size_t batch, int scalars_mont, void* d_out_xy) {
   if (!ctx || !srs || !d_out_xy || (!d_scalars && n)) return CAPGPU_ERR_ARG;
   return guarded(ctx, [&] {
-    msm_device(ctx, srs, base_off, (const Fr*)d_scalars, n, n, batch, scalars_mont != 0, (G1Affine*)d_out_xy);
+    msm_device(ctx, srs, base_off, (const Fr*)d_scalars, n, n, batch, scalars_mont != 0, (G1Affine*)d_out_xy, true);
   });
 }

@@ -140,7 +140,7 @@ void round1(capgpu_job* job, const uint64_t* blinders10, uint64_t* wire_comms) {
   memcpy(ba.b, blinders10, 10 * sizeof(Fr));
   ba.rows_blinded = 5;
   blind(ctx, job->polys, NP, n, 6, 2, ba);
-  msm_device(ctx, pk->srs, 0, job->polys, n + 2, NP, 5, true, job->comms_dev);
+  msm_device(ctx, pk->srs, 0, job->polys, n + 2, NP, 5, true, job->comms_dev, ctx->latency_mode);
   read_points(job, 5, wire_comms);
   job->round = 2;
 }
@@ -163,7 +163,7 @@ void round2(capgpu_job* job, const uint64_t* beta, const uint64_t* gamma, const 
   memcpy(ba.b, blinders3, 3 * sizeof(Fr));
   ba.rows_blinded = 1;
   blind(ctx, zp, NP, n, 1, 3, ba);
-  msm_device(ctx, pk->srs, 0, zp, n + 3, NP, 1, true, job->comms_dev);
+  msm_device(ctx, pk->srs, 0, zp, n + 3, NP, 1, true, job->comms_dev, ctx->latency_mode);
   read_points(job, 1, z_comm);
   job->round = 3;
 }
@@ -189,7 +189,7 @@ void round3(capgpu_job* job, const uint64_t* alpha, const uint64_t* blinders4, u
   memcpy(ba.b, blinders4, 4 * sizeof(Fr));
   ba.rows_blinded = 4;
   split_quotient(ctx, job->t, n, m, job->split, NP, ba, job->flag);
-  msm_device(ctx, pk->srs, 0, job->split, n + 3, NP, 5, true, job->comms_dev);
+  msm_device(ctx, pk->srs, 0, job->split, n + 3, NP, 5, true, job->comms_dev, ctx->latency_mode);
   uint8_t* pin = static_cast<uint8_t*>(ctx->pinned);
   CAPGPU_CUDA(cudaMemcpyAsync(pin + 1024, job->flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   read_points(job, 5, split_comms);
@@ -258,7 +258,7 @@ void round5(capgpu_job* job, const uint64_t* v_in, uint64_t* opening_comms) {
   da.src[1] = job->polys + 6 * NP; da.dst[1] = job->shifted; da.len[1] = n + 3; da.x[1] = to_dev(zeta_w); da.xinv[1] = to_dev(zeta_w.inv());
   divide_linear(ctx, da, 2, job->div_scratch, job->div_tmax);
   // open and shifted are adjacent rows of stride NP
-  msm_device(ctx, pk->srs, 0, job->open, n + 2, NP, 2, true, job->comms_dev);
+  msm_device(ctx, pk->srs, 0, job->open, n + 2, NP, 2, true, job->comms_dev, ctx->latency_mode);
   read_points(job, 2, opening_comms);
   job->round = 6;
 }

@@ -54,6 +54,11 @@ const char* capgpu_last_error(const capgpu_ctx* ctx);
 int capgpu_ctx_create(int device, capgpu_ctx** out);
 void capgpu_ctx_destroy(capgpu_ctx* ctx);
 int capgpu_ctx_sync(capgpu_ctx* ctx);
+/* Scheduling preference of the prover's internal MSMs: 0 (default) minimises total GPU work per
+ * proof (best proofs/s with several contexts per GPU), 1 minimises the depth of each MSM's
+ * bucket reduction (best single-proof latency).  Results are identical either way.  The
+ * standalone capgpu_msm_g1 / capgpu_msm_g1_dev calls always use the low-latency schedule. */
+int capgpu_ctx_set_latency_mode(capgpu_ctx* ctx, int on);
 /* Raw cudaStream_t of the ctx (for callers that time with CUDA events). */
 void* capgpu_ctx_stream(capgpu_ctx* ctx);
 
