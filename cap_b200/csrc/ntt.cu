@@ -270,6 +270,12 @@ __host__ __device__ constexpr int ntt_phase_start(int log_t, int ph) {
 
 __device__ __forceinline__ uint32_t ntt_pad(uint32_t pos) { return pos + (pos >> 3); }
 
+// Out-of-line Montgomery product for the register-radix kernel: with ~40 products per thread
+// fully inlined the kernel body is ~160 KB of SASS and small launches stall on instruction
+// fetch (ncu: no_instruction 5.8 cycles per issue); one shared copy keeps the body in the
+// instruction cache.  Arguments and result travel in registers (by value).
+__device__ __noinline__ Fr ntt_mul(Fr a, Fr b) { return fp_mul(a, b); }
+
 // position of element `slot` of thread t in the phase starting at stage S with RR stages
 template <int LOG_T, int S, int RR>
 __device__ __forceinline__ uint32_t ntt_slot_pos(uint32_t t, int slot) {
@@ -304,7 +310,7 @@ __device__ __forceinline__ void ntt_phase_butterflies(Fr (&x)[8], uint32_t t, co
         Fr d = fp_sub(va, vb);
         if (log_m > 0) {
           const uint32_t k = lo + ((uint32_t)(i & (half - 1)) << LOG_STRIDE);
-          d = fp_mul(d, tw[k << (9 - log_m)]);
+          d = ntt_mul(d, tw[k << (9 - log_m)]);
         }
         x[b] = d;
       }
@@ -354,7 +360,7 @@ __global__ void __launch_bounds__(256, 2) ntt_reg_kernel(NttPass P) {
     const uint32_t idx = pos * P.in_p_stride + gcol * P.in_g_stride;
     if (idx < P.src_len) {
       x[e] = src[idx];
-      if (P.pre) x[e] = fp_mul(x[e], P.pre[pos]);
+      if (P.pre) x[e] = ntt_mul(x[e], P.pre[pos]);
     } else {
       x[e] = Fr::zero();
     }
@@ -368,7 +374,7 @@ __global__ void __launch_bounds__(256, 2) ntt_reg_kernel(NttPass P) {
     const uint32_t q = __brev(pos) >> (32 - LOG_T);
     const uint32_t oidx = q * P.out_q_stride + gcol * P.out_g_stride;
     Fr v = x[e];
-    if (P.post) v = fp_mul(v, P.post[oidx]);
+    if (P.post) v = ntt_mul(v, P.post[oidx]);
     dst[oidx] = v;
   }
 }
@@ -381,11 +387,8 @@ static void launch_reg_pass(capgpu_ctx* ctx, NttPass p, size_t n, size_t batch) 
   p.log_g = log_g;
   const uint32_t G = 1u << log_g;
   size_t smem = (size_t)8 * G * TP * sizeof(uint32_t);
-  static bool attr_set = false;
-  if (!attr_set) {
-    CAPGPU_CUDA(cudaFuncSetAttribute(ntt_reg_kernel<LOG_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2048 / T * TP * 4));
-    attr_set = true;
-  }
+  // per device, idempotent and cheap: set on every launch (contexts of several GPUs may share the process)
+  CAPGPU_CUDA(cudaFuncSetAttribute(ntt_reg_kernel<LOG_T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2048 / T * TP * 4));
   dim3 grid((unsigned)(n / ((size_t)T * G)), (unsigned)batch);
   ProfScope prof(ctx, PROF_NTT, (double)batch * (double)(n / 2) * LOG_T);
   ntt_reg_kernel<LOG_T><<<grid, G * T / 8, smem, ctx->stream>>>(p);

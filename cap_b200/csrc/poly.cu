@@ -66,21 +66,26 @@ __global__ void gp_chunk_prod(const Fr* __restrict__ num, const Fr* __restrict__
   cd[t] = pd;
 }
 
-// One block, T (<= 1024) threads.  Out: cn[t] = prod_{u<t} cn_in[u] (numerator prefix at the
-// chunk start), cd[t] = 1 / prod_{u<=t} cd_in[u] (inverse denominator prefix at the chunk end).
+// One block of 1024 threads over T chunk products (each thread owns `per` consecutive chunks).
+// Out: cn[t] = prod_{u<t} cn_in[u] (numerator prefix at the chunk start),
+//      cd[t] = 1 / prod_{u<=t} cd_in[u] (inverse denominator prefix at the chunk end).
 __global__ void __launch_bounds__(1024) gp_scan(Fr* cn, Fr* cd, int T) {
   extern __shared__ uint32_t gp_sm[];
-  Fr* sn = reinterpret_cast<Fr*>(gp_sm);  // T entries
-  Fr* sd = sn + T;                        // T entries
+  Fr* sn = reinterpret_cast<Fr*>(gp_sm);  // 1024 entries
+  Fr* sd = sn + 1024;                     // 1024 entries
   __shared__ Fr inv_total;
   const int t = threadIdx.x;
-  Fr myd = Fr::one();
-  if (t < T) { sn[t] = cn[t]; myd = cd[t]; sd[t] = myd; }
+  const int per = (T + 1023) / 1024;
+  const int lo = t * per, hi = lo + per < T ? lo + per : T;
+  Fr pn = Fr::one(), pd = Fr::one();
+  for (int i = lo; i < hi; i++) { pn = fp_mul(pn, cn[i]); pd = fp_mul(pd, cd[i]); }
+  sn[t] = pn;
+  sd[t] = pd;
   __syncthreads();
   // inclusive prefix product of sn, inclusive suffix product of sd (Hillis-Steele)
-  for (int o = 1; o < T; o <<= 1) {
+  for (int o = 1; o < 1024; o <<= 1) {
     Fr a, b;
-    bool ha = t < T && t >= o, hb = t < T && t + o < T;
+    bool ha = t >= o, hb = t + o < 1024;
     if (ha) a = sn[t - o];
     if (hb) b = sd[t + o];
     __syncthreads();
@@ -90,10 +95,19 @@ __global__ void __launch_bounds__(1024) gp_scan(Fr* cn, Fr* cd, int T) {
   }
   if (t == 0) inv_total = fp_inv(sd[0]);
   __syncthreads();
-  if (t < T) {
-    cn[t] = t == 0 ? Fr::one() : sn[t - 1];
-    // 1 / prod_{u<=t} d_u = inv_total * prod_{u>t} d_u
-    cd[t] = t + 1 < T ? fp_mul(inv_total, sd[t + 1]) : inv_total;
+  // numerators: forward from the exclusive prefix of this thread
+  Fr run = t == 0 ? Fr::one() : sn[t - 1];
+  for (int i = lo; i < hi; i++) {
+    Fr cur = cn[i];
+    cn[i] = run;
+    run = fp_mul(run, cur);
+  }
+  // denominators: backward from inv_total * (product of everything right of this thread)
+  Fr rd = t + 1 < 1024 ? fp_mul(inv_total, sd[t + 1]) : inv_total;
+  for (int i = hi; i-- > lo;) {
+    Fr cur = cd[i];
+    cd[i] = rd;  // 1 / prod_{u<=i} d_u = inv_total * prod_{u>i} d_u
+    rd = fp_mul(rd, cur);
   }
 }
 
@@ -116,21 +130,16 @@ __global__ void gp_finish(const Fr* __restrict__ num, const Fr* __restrict__ den
 
 void grand_product(capgpu_ctx* ctx, const Fr* wires, size_t wstride, const Fr* sig_eval, const Fr* omega_pows, size_t n,
                    const GpArgs& a, Fr* num, Fr* den, Fr* cn, Fr* cd, Fr* z) {
-  size_t T = n / 2 < 1024 ? n / 2 : 1024;
-  if (T < 1) T = 1;
-  size_t L = n / T;
+  // chunks of 8 rows (fewer for tiny domains): T = n / L chunk products, scanned by one CTA
+  size_t L = n >= 16 ? 8 : 1;
+  size_t T = n / L;
   ProfScope prof(ctx, PROF_GRAND_PRODUCT, (double)n);
   gp_terms<<<ceil_div(n, 128), 128, 0, ctx->stream>>>(wires, wstride, sig_eval, omega_pows, n, a, num, den);
   CAPGPU_LAUNCH_CHECK(ctx);
   gp_chunk_prod<<<ceil_div(T, 128), 128, 0, ctx->stream>>>(num, den, n, L, cn, cd);
   CAPGPU_LAUNCH_CHECK(ctx);
-  unsigned threads = (unsigned)((T + 31) / 32 * 32);
-  static bool attr_set = false;
-  if (!attr_set) {
-    CAPGPU_CUDA(cudaFuncSetAttribute(gp_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 1024 * (int)sizeof(Fr)));
-    attr_set = true;
-  }
-  gp_scan<<<1, threads, 2 * T * sizeof(Fr), ctx->stream>>>(cn, cd, (int)T);
+  CAPGPU_CUDA(cudaFuncSetAttribute(gp_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 1024 * (int)sizeof(Fr)));
+  gp_scan<<<1, 1024, 2 * 1024 * sizeof(Fr), ctx->stream>>>(cn, cd, (int)T);
   CAPGPU_LAUNCH_CHECK(ctx);
   gp_finish<<<ceil_div(T, 128), 128, 0, ctx->stream>>>(num, den, n, L, cn, cd, z);
   CAPGPU_LAUNCH_CHECK(ctx);

@@ -80,7 +80,7 @@ capgpu_job* job_acquire(capgpu_ctx* ctx, const capgpu_pk* pk) {
     job->num_inputs = pk->num_inputs;
     const size_t n = job->n, m = job->m, NP = job->NP;
     job->div_tmax = (NP + 15) / 16 + 1;
-    size_t elems = 6 * n + 7 * NP + n + 7 * m + m + 5 * NP + 4 * NP + 2 * n + 2 * 1024 + 7 * m + 16 + 160 + 2 * job->div_tmax +
+    size_t elems = 6 * n + 7 * NP + n + 7 * m + m + 5 * NP + 4 * NP + 2 * n + 2 * (n / 8 + 8) + 7 * m + 16 + 160 + 2 * job->div_tmax +
                    align_up(pk->num_inputs + 1, 8);
     size_t bytes = elems * sizeof(Fr) + 8 * sizeof(G1Affine) + 256;
     job->buf.reserve(bytes);
@@ -94,7 +94,7 @@ capgpu_job* job_acquire(capgpu_ctx* ctx, const capgpu_pk* pk) {
     job->split = take(5 * NP);
     job->lin = take(NP); job->batch = take(NP); job->open = take(NP); job->shifted = take(NP);
     job->num = take(n); job->den = take(n);
-    job->cn = take(1024); job->cd = take(1024);
+    job->cn = take(n / 8 + 8); job->cd = take(n / 8 + 8);
     job->ntt_tmp = take(7 * m);
     job->evals_dev = take(16);
     job->eval_scratch = take(160);

@@ -195,3 +195,28 @@ def test_transfer_shape_proofs_are_accepted(ctx):
         assert kzg_commit_tau(wp[:circ.n + 2], TAU) == proof["wires_poly_comms"][0]
     pk.close()
     srs.close()
+
+
+def test_device_resident_and_latency_mode_give_identical_proofs(ctx):
+    """capgpu_prove_dev (witness columns already in HBM) and the low-latency MSM schedule are
+    scheduling choices only: the proof bytes are identical to the default path."""
+    import torch
+    circ = synth.make_circuit(10, num_inputs=5, seed=4)
+    srs = plonk.PlonkKzgSnark.universal_setup(ctx, circ.n + 2, TAU)
+    pk = plonk.PlonkKzgSnark.preprocess(ctx, srs, circ)
+    wires = plonk.wire_values(circ)
+    pub = field.fr_to_mont_array(plonk.public_input(circ))
+    bl = field.fr_raw_array(_mont(list(range(3, 20))))
+    base = plonk.PlonkKzgSnark.prove_raw(ctx, pk, wires, pub, bl, b"x")
+    lib = ctx.lib
+    assert lib.capgpu_ctx_set_latency_mode(ctx.h, 1) == 0
+    lat = plonk.PlonkKzgSnark.prove_raw(ctx, pk, wires, pub, bl, b"x")
+    assert lib.capgpu_ctx_set_latency_mode(ctx.h, 0) == 0
+    assert bytes(lat) == bytes(base)
+    dw = torch.from_numpy(wires.view(np.int64)).cuda()
+    msg = (ctypes.c_uint8 * 1).from_buffer_copy(b"x")
+    out = _lib.Proof()
+    _lib.check(lib.capgpu_prove_dev(ctx.h, pk.h, c_void_p(dw.data_ptr()), _ptr(pub), _ptr(bl), msg, 1, byref(out)), ctx.h)
+    assert bytes(out) == bytes(base)
+    pk.close()
+    srs.close()
