@@ -85,7 +85,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -179,7 +179,9 @@ def run_capgpu(args):
     def timed(on_device: bool, sample_clocks: bool):
         for _ in range(args.warmup):
             step(on_device)
-        sampler = ClockSampler(local) if sample_clocks else None
+        # one sampler per job (rank 0's GPU): eight nvidia-smi pollers contend on the driver and
+        # visibly slow multi-GPU runs
+        sampler = ClockSampler(local) if (sample_clocks and rank == 0) else None
         launches0 = sum(c.launch_count for c in ctxs)
         barrier()
         if sampler:

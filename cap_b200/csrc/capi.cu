@@ -35,6 +35,7 @@ extern "C" int capgpu_ctx_create(int device, capgpu_ctx** out) {
     ctx->sm_count = prop.multiProcessorCount;
     ctx->pinned_bytes = 1 << 16;
     CAPGPU_CUDA(cudaMallocHost(&ctx->pinned, ctx->pinned_bytes));
+    CAPGPU_CUDA(cudaEventCreateWithFlags(&ctx->sync_ev, cudaEventBlockingSync | cudaEventDisableTiming));
   });
   if (rc != CAPGPU_OK) { delete ctx; return rc; }
   *out = ctx;
@@ -51,6 +52,9 @@ extern "C" void capgpu_ctx_destroy(capgpu_ctx* ctx) {
   ctx->msm_scalars.release(); ctx->msm_digits.release(); ctx->msm_counts.release();
   ctx->msm_entries.release(); ctx->msm_buckets.release(); ctx->msm_partials.release(); ctx->msm_out.release();
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->sync_ev) cudaEventDestroy(ctx->sync_ev);
+  if (ctx->pe0) cudaEventDestroy(ctx->pe0);
+  if (ctx->pe1) cudaEventDestroy(ctx->pe1);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

@@ -60,6 +60,7 @@ struct capgpu_ctx {
   // workspaces
   capgpu::DevBuf ntt_tmp, ntt_io;
   capgpu::DevBuf msm_scalars, msm_digits, msm_counts, msm_entries, msm_buckets, msm_partials, msm_out;
+  cudaEvent_t sync_ev = nullptr;  // cudaEventBlockingSync: host threads sleep while a round runs
   void* pinned = nullptr;  // small pinned staging area
   size_t pinned_bytes = 0;
   // optional per-kernel timing (capgpu_profile_enable): CUDA events on the ctx stream around
@@ -111,6 +112,19 @@ int guarded(capgpu_ctx* ctx, F&& f) {
 }
 
 #define CAPGPU_LAUNCH_CHECK(ctx) do { (ctx)->launches++; CAPGPU_CUDA(cudaGetLastError()); } while (0)
+
+// Waits for everything queued on the ctx stream.  In the default (throughput) mode the host
+// thread blocks on an event created with cudaEventBlockingSync instead of spinning, so several
+// prover contexts per GPU (and several GPUs per host) do not burn a core each between rounds;
+// latency mode keeps the lower-latency spinning synchronise.
+inline void ctx_wait(capgpu_ctx* ctx) {
+  if (ctx->latency_mode || !ctx->sync_ev) {
+    CAPGPU_CUDA(cudaStreamSynchronize(ctx->stream));
+    return;
+  }
+  CAPGPU_CUDA(cudaEventRecord(ctx->sync_ev, ctx->stream));
+  CAPGPU_CUDA(cudaEventSynchronize(ctx->sync_ev));
+}
 
 inline unsigned ceil_div(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
 

@@ -43,7 +43,8 @@ __device__ __forceinline__ uint32_t subc_cc(uint32_t a, uint32_t b) { uint32_t r
 __device__ __forceinline__ uint32_t subc(uint32_t a, uint32_t b) { uint32_t r; asm volatile("subc.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 // 64-bit wide multiply(-add) on a register pair (lo, hi)
 __device__ __forceinline__ void mul_wide(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {
-  asm volatile("mul.lo.u32 %0, %2, %3; mul.hi.u32 %1, %2, %3;" : "=&r"(lo), "=r"(hi) : "r"(a), "r"(b));
+  // one IMAD.WIDE.U32 (mul.lo + mul.hi would lower to IMAD + IMAD.HI: two fma-pipe slots)
+  asm volatile("{.reg .u64 t; mul.wide.u32 t, %2, %3; mov.b64 {%0, %1}, t;}" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
 }
 // (lo,hi) += a*b, starts a carry chain (no carry-in), leaves carry-out
 __device__ __forceinline__ void mad_wide_cc(uint32_t& lo, uint32_t& hi, uint32_t a, uint32_t b) {

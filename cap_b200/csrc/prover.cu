@@ -125,7 +125,7 @@ void job_begin(capgpu_job* job, const uint64_t* wires, const uint64_t* pub_input
 void read_points(capgpu_job* job, int count, uint64_t* out_xy) {
   capgpu_ctx* ctx = job->ctx;
   CAPGPU_CUDA(cudaMemcpyAsync(ctx->pinned, job->comms_dev, count * sizeof(G1Affine), cudaMemcpyDeviceToHost, ctx->stream));
-  CAPGPU_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx_wait(ctx);
   memcpy(out_xy, ctx->pinned, count * sizeof(G1Affine));
 }
 
@@ -212,7 +212,7 @@ void round4(capgpu_job* job, const uint64_t* zeta, uint64_t* evals_out) {
   ea.poly[9] = job->polys + 6 * NP; ea.len[9] = n + 3; ea.x[9] = to_dev(zeta_w);
   evaluate(ctx, ea, 10, job->evals_dev, job->eval_scratch);
   CAPGPU_CUDA(cudaMemcpyAsync(ctx->pinned, job->evals_dev, 10 * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
-  CAPGPU_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx_wait(ctx);
   memcpy(evals_out, ctx->pinned, 10 * sizeof(Fr));
   for (int i = 0; i < 10; i++) job->evals[i] = HFr::from_limbs(evals_out + 4 * i);
   job->round = 5;
@@ -290,7 +290,7 @@ void pk_finish(capgpu_ctx* ctx, capgpu_pk* pk) {
     x = x * wm;
   }
   CAPGPU_CUDA(cudaMemcpyAsync(pk->zh_inv, zh, sizeof zh, cudaMemcpyHostToDevice, ctx->stream));
-  CAPGPU_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx_wait(ctx);
   // transcript bytes of the verifying key (SolidityTranscript::append_vk_and_pub_input, minus the inputs)
   SolidityTranscript t;
   t.append_u64_le(254);
