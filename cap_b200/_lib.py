@@ -19,7 +19,7 @@ EXPORTS = [
     "capgpu_ntt", "capgpu_pk_upload", "capgpu_preprocess", "capgpu_pk_export", "capgpu_pk_destroy",
     "capgpu_prove", "capgpu_job_begin", "capgpu_job_round1", "capgpu_job_round2", "capgpu_job_round3",
     "capgpu_job_round4", "capgpu_job_round5", "capgpu_job_end", "capgpu_debug_read", "capgpu_launch_count",
-    "capgpu_calibrate", "capgpu_prove_dev", "capgpu_profile_enable", "capgpu_profile_read", "capgpu_ctx_set_latency_mode",
+    "capgpu_calibrate", "capgpu_prove_dev", "capgpu_profile_enable", "capgpu_profile_read", "capgpu_ctx_set_latency_mode", "capgpu_g1_sum_dev",
 ]
 
 
@@ -71,6 +71,7 @@ def load() -> ctypes.CDLL:
         "capgpu_srs_export": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t]),
         "capgpu_msm_g1_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, c_int, c_void_p]),
         "capgpu_ntt_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_uint, c_size_t, c_int, c_int]),
+        "capgpu_g1_sum_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
         "capgpu_srs_destroy": (None, [c_void_p]),
         "capgpu_srs_size": (c_size_t, [c_void_p]),
         "capgpu_msm_g1": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, c_int, c_void_p]),

@@ -485,3 +485,32 @@ extern "C" int capgpu_msm_g1_dev(capgpu_ctx* ctx, const capgpu_srs* srs, size_t 
     msm_device(ctx, srs, base_off, (const Fr*)d_scalars, n, n, batch, scalars_mont != 0, (G1Affine*)d_out_xy, true);
   });
 }
+
+// ------------------------------------------------------------------------------------------
+// Sum of a few affine points (the fold of a point-range-split MSM: every GPU contributes the
+// 64-byte result of its slice, gathered over NVLink; EC addition is not an NCCL reduction op,
+// so it is gather-then-add).  One warp.
+// ------------------------------------------------------------------------------------------
+namespace capgpu {
+__global__ void g1_sum_kernel(const G1Affine* __restrict__ pts, uint32_t count, G1Affine* out) {
+  G1XYZZ v = G1XYZZ::inf();
+  for (uint32_t i = threadIdx.x; i < count; i += 32) {
+    G1Affine p = pts[i];
+    if (!p.is_inf()) xyzz_add_mixed(v, p.x, p.y, false);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    G1XYZZ other = shfl_down_xyzz(v, o, 32);
+    xyzz_add(v, other);
+  }
+  if (threadIdx.x == 0) *out = xyzz_to_affine(v);
+}
+}  // namespace capgpu
+
+extern "C" int capgpu_g1_sum_dev(capgpu_ctx* ctx, const void* d_points_xy, size_t count, void* d_out_xy) {
+  if (!ctx || !d_out_xy || (!d_points_xy && count)) return CAPGPU_ERR_ARG;
+  return guarded(ctx, [&] {
+    CAPGPU_REQUIRE(count <= (1u << 20), "too many points");
+    g1_sum_kernel<<<1, 32, 0, ctx->stream>>>((const G1Affine*)d_points_xy, (uint32_t)count, (G1Affine*)d_out_xy);
+    CAPGPU_LAUNCH_CHECK(ctx);
+  });
+}

@@ -91,6 +91,11 @@ int capgpu_msm_g1(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const
 int capgpu_msm_g1_dev(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const void* d_scalars, size_t n,
                       size_t batch, int scalars_mont, void* d_out_xy);
 
+/* Sum of `count` affine points resident on the device (asynchronous on the ctx stream).  Used to
+ * fold a point-range-split MSM: each GPU runs capgpu_msm_g1_dev over its slice of the bases, the
+ * 64-byte partial results are gathered over NVLink (NCCL all-gather) and added here. */
+int capgpu_g1_sum_dev(capgpu_ctx* ctx, const void* d_points_xy, size_t count, void* d_out_xy);
+
 /* ---- radix-2 NTT over Fr -----------------------------------------------------------------
  * Replaces ark-poly 0.3.0 `Radix2EvaluationDomain::{fft, ifft, coset_fft, coset_ifft}`
  * (natural order in and out, coset shift = Fr::multiplicative_generator() = 5, ifft includes

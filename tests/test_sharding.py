@@ -55,3 +55,52 @@ def test_two_rank_gloo_timing_reduction():
 
 def test_no_group_is_identity():
     assert shard.reduce_timing(3.5, 7) == (3.5, 7)
+
+
+def test_point_range_partition():
+    for world in (1, 2, 3, 8):
+        for n in (1, 17, 1 << 17):
+            rs = [shard.point_range(n, world, r) for r in range(world)]
+            assert rs[0][0] == 0 and rs[-1][1] == n
+            assert all(rs[i][1] == rs[i + 1][0] for i in range(world - 1))
+
+
+def _split_worker(rank, world, port, q):
+    """Point-range split of one MSM: partial sums per rank (oracle arithmetic stands in for the
+    GPU here), one all-gather of the 64-byte results, EC fold on every rank."""
+    import random
+    from oracle import bn254 as B
+    from oracle import msm as omsm
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    n, tau = 37, 123456789
+    rng = random.Random(1)
+    scalars = [rng.randrange(B.R) for _ in range(n)]
+    bases = B.srs_powers(tau, n)
+    lo, hi = shard.point_range(n, world, rank)
+    part = omsm.msm_naive(bases[lo:hi], scalars[lo:hi])
+    gathered = [None] * world
+    dist.all_gather_object(gathered, part)
+    total = None
+    for p in gathered:
+        total = B.g1_add(total, p)
+    if rank == 0:
+        q.put(total == omsm.kzg_commit_tau(scalars, tau))
+    dist.destroy_process_group()
+
+
+def test_split_msm_fold_two_ranks_gloo():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    procs = [ctx.Process(target=_split_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get() is True
