@@ -58,6 +58,47 @@ __global__ void msm_setup_powers(G1Affine* table, size_t n, Fr tau) {
   table[i] = xyzz_to_affine(acc);
 }
 
+// ark-serialize 0.3 compressed G1 (32 bytes: x little-endian, bit 255 = "y is the larger of
+// {y, -y}", bit 254 = infinity) -> affine Montgomery.  The form `UniversalSrs` / `ProvingKey` files
+// hold their points in (/root/reference/src/parameters.rs:557-592, src/proof/mod.rs:106).
+// y = (x^3 + 3)^((q+1)/4) since q = 3 mod 4; flag[0] is set if some x is not on the curve.
+__global__ void msm_decompress(const uint32_t* __restrict__ bytes, G1Affine* table, size_t n, uint32_t* flag) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t EXP[8] = {0xb61f3f52u, 0x4f082305u, 0x5a1c72a3u, 0x65e05aa4u, 0xa0605617u, 0x6e14116du, 0xb84c680au, 0x0c19139cu};   // (q+1)/4
+  const uint32_t HALF[8] = {0x6c3e7ea3u, 0x9e10460bu, 0xb438e546u, 0xcbc0b548u, 0x40c0ac2eu, 0xdc2822dbu, 0x7098d014u, 0x18322739u};  // (q-1)/2
+  Fq xc;
+  for (int l = 0; l < 8; l++) xc.v[l] = bytes[i * 8 + l];
+  const uint32_t flags = xc.v[7] >> 30;
+  xc.v[7] &= 0x3fffffffu;
+  G1Affine out;
+  if (flags & 1u) {  // infinity
+    out.x = Fq::zero(); out.y = Fq::zero();
+    table[i] = out;
+    return;
+  }
+  // canonical x must be < q
+  bool lt = false;
+  for (int l = 7; l >= 0; l--) {
+    uint32_t pl = FqParams::p(l);
+    if (xc.v[l] != pl) { lt = xc.v[l] < pl; break; }
+  }
+  Fq x = fp_to_mont(xc);
+  Fq three = fp_add(fp_dbl(Fq::one()), Fq::one());
+  Fq rhs = fp_add(fp_mul(fp_sqr(x), x), three);
+  Fq y = fp_pow(rhs, EXP);
+  if (!lt || fp_sqr(y) != rhs) { atomicOr(flag, 1u); out.x = Fq::zero(); out.y = Fq::zero(); table[i] = out; return; }
+  // "positive" = canonical y > (q-1)/2
+  Fq yc = fp_from_mont(y);
+  bool larger = false;
+  for (int l = 7; l >= 0; l--) {
+    if (yc.v[l] != HALF[l]) { larger = yc.v[l] > HALF[l]; break; }
+  }
+  if (larger != ((flags & 2u) != 0)) y = fp_neg(y);
+  out.x = x; out.y = y;
+  table[i] = out;
+}
+
 // ------------------------------------------------------------------------------------------
 // recode + histogram
 // ------------------------------------------------------------------------------------------
@@ -286,7 +327,7 @@ struct MsmTuning {
 
 static const MsmTuning& msm_tuning() {
   static MsmTuning t = [] {
-    MsmTuning x{0, 131072};
+    MsmTuning x{0, 65536};  // measured: a 2^17-point MSM runs 7 % faster with 2 lanes per bucket than with 4
     if (const char* e = getenv("CAPGPU_RED_SEG")) x.red_seg = atoi(e);
     if (const char* e = getenv("CAPGPU_ACC_THREADS")) x.acc_threads = (size_t)atol(e);
     return x;
@@ -395,16 +436,22 @@ void msm_device(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const F
 
 using namespace capgpu;
 
-static int srs_create(capgpu_ctx* ctx, const uint64_t* points_xy, const uint64_t* tau, size_t n_points, int window_bits, capgpu_srs** out);
+static int srs_create(capgpu_ctx* ctx, const uint64_t* points_xy, const uint64_t* tau, const uint8_t* compressed, size_t n_points,
+                      int window_bits, capgpu_srs** out);
 
 extern "C" int capgpu_srs_upload(capgpu_ctx* ctx, const uint64_t* points_xy, size_t n_points, int window_bits, capgpu_srs** out) {
   if (!ctx || !out || !points_xy) return CAPGPU_ERR_ARG;
-  return srs_create(ctx, points_xy, nullptr, n_points, window_bits, out);
+  return srs_create(ctx, points_xy, nullptr, nullptr, n_points, window_bits, out);
 }
 
 extern "C" int capgpu_srs_setup(capgpu_ctx* ctx, const uint64_t* tau, size_t n_points, int window_bits, capgpu_srs** out) {
   if (!ctx || !out || !tau) return CAPGPU_ERR_ARG;
-  return srs_create(ctx, nullptr, tau, n_points, window_bits, out);
+  return srs_create(ctx, nullptr, tau, nullptr, n_points, window_bits, out);
+}
+
+extern "C" int capgpu_srs_upload_compressed(capgpu_ctx* ctx, const uint8_t* bytes, size_t n_points, int window_bits, capgpu_srs** out) {
+  if (!ctx || !out || !bytes) return CAPGPU_ERR_ARG;
+  return srs_create(ctx, nullptr, nullptr, bytes, n_points, window_bits, out);
 }
 
 extern "C" int capgpu_srs_export(capgpu_ctx* ctx, const capgpu_srs* srs, uint64_t* points_xy, size_t n_points) {
@@ -416,7 +463,8 @@ extern "C" int capgpu_srs_export(capgpu_ctx* ctx, const capgpu_srs* srs, uint64_
   });
 }
 
-static int srs_create(capgpu_ctx* ctx, const uint64_t* points_xy, const uint64_t* tau, size_t n_points, int window_bits, capgpu_srs** out) {
+static int srs_create(capgpu_ctx* ctx, const uint64_t* points_xy, const uint64_t* tau, const uint8_t* compressed, size_t n_points,
+                      int window_bits, capgpu_srs** out) {
   *out = nullptr;
   capgpu_srs* srs = new capgpu_srs();
   int rc = guarded(ctx, [&] {
@@ -437,6 +485,22 @@ static int srs_create(capgpu_ctx* ctx, const uint64_t* points_xy, const uint64_t
     CAPGPU_CUDA(cudaMalloc(&srs->table, (size_t)srs->W * n_points * sizeof(G1Affine)));
     if (points_xy) {
       CAPGPU_CUDA(cudaMemcpyAsync(srs->table, points_xy, n_points * sizeof(G1Affine), cudaMemcpyHostToDevice, ctx->stream));
+    } else if (compressed) {
+      // stage the 32-byte encodings in the (not yet used) upper part of the table allocation
+      uint32_t* stage = reinterpret_cast<uint32_t*>(srs->table + n_points * (srs->W > 1 ? 1 : 0));
+      DevBuf tmp;
+      if (srs->W == 1) { tmp.reserve(n_points * 32); stage = tmp.as<uint32_t>(); }
+      ctx->msm_counts.reserve(sizeof(uint32_t));
+      uint32_t* flag = ctx->msm_counts.as<uint32_t>();
+      CAPGPU_CUDA(cudaMemsetAsync(flag, 0, sizeof(uint32_t), ctx->stream));
+      CAPGPU_CUDA(cudaMemcpyAsync(stage, compressed, n_points * 32, cudaMemcpyHostToDevice, ctx->stream));
+      msm_decompress<<<ceil_div(n_points, 64), 64, 0, ctx->stream>>>(stage, srs->table, n_points, flag);
+      CAPGPU_LAUNCH_CHECK(ctx);
+      uint32_t bad = 0;
+      CAPGPU_CUDA(cudaMemcpyAsync(&bad, flag, sizeof bad, cudaMemcpyDeviceToHost, ctx->stream));
+      CAPGPU_CUDA(cudaStreamSynchronize(ctx->stream));
+      tmp.release();
+      CAPGPU_REQUIRE(bad == 0, "compressed SRS contains a point that is not on the curve");
     } else {
       Fr t;
       memcpy(t.v, tau, sizeof t.v);

@@ -80,13 +80,19 @@ class Context:
 class Srs:
     """Device-resident commit key (``powers_of_g``), with the MSM's window-shifted tables."""
 
-    def __init__(self, ctx: Context, points_xy=None, window_bits: int = 0, tau_mont=None, size: int = 0):
-        """Either upload ``points_xy`` ((n, 8) uint64) or generate tau^i * g on the device
+    def __init__(self, ctx: Context, points_xy=None, window_bits: int = 0, tau_mont=None, size: int = 0, compressed=None):
+        """Upload ``points_xy`` ((n, 8) uint64), or ``compressed`` (n x 32 bytes of ark-serialize
+        compressed G1 points, decompressed on the device), or generate tau^i * g on the device
         from ``tau_mont`` ((4,) uint64 Montgomery limbs) for ``size`` points."""
         self.ctx = ctx
         self.lib = ctx.lib
         h = c_void_p()
-        if points_xy is not None:
+        if compressed is not None:
+            raw = np.frombuffer(bytes(compressed), dtype=np.uint8)
+            assert raw.size % 32 == 0, "compressed G1 points are 32 bytes each"
+            _lib.check(self.lib.capgpu_srs_upload_compressed(ctx.h, _ptr(raw), raw.size // 32, window_bits, byref(h)), ctx.h)
+            self.size = raw.size // 32
+        elif points_xy is not None:
             pts = _as_u64(points_xy, 8)
             _lib.check(self.lib.capgpu_srs_upload(ctx.h, _ptr(pts), pts.shape[0], window_bits, byref(h)), ctx.h)
             self.size = pts.shape[0]

@@ -68,6 +68,11 @@ void* capgpu_ctx_stream(capgpu_ctx* ctx);
  * precomputes the window-shifted copies 2^(c*w) * P_i used by the MSM. `window_bits` = 0
  * lets the library choose.  */
 int capgpu_srs_upload(capgpu_ctx* ctx, const uint64_t* points_xy, size_t n_points, int window_bits, capgpu_srs** out);
+/* Same from ark-serialize 0.3 *compressed* points (32 bytes each: x little-endian, bit 255 = y is
+ * the larger root, bit 254 = infinity), the encoding of the `powers_of_g` vector inside the SRS /
+ * proving-key files of /root/reference/src/parameters.rs:557-592 and the Aztec CRS that
+ * src/proof/mod.rs:74-109 deserialises; decompression (square root in Fq) runs on the device. */
+int capgpu_srs_upload_compressed(capgpu_ctx* ctx, const uint8_t* bytes, size_t n_points, int window_bits, capgpu_srs** out);
 /* `KZG10::setup` on the device (PlonkKzgSnark::universal_setup, src/proof/mod.rs:59-69, minus
  * the RNG): powers_of_g[i] = tau^i * g for the caller's tau (Fr, Montgomery) and g = (1, 2).
  * Used for synthetic SRS in tests / benches (the Aztec CRS blob is not shipped). */

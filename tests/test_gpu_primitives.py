@@ -173,3 +173,22 @@ def test_msm_at_bench_sizes(ctx, log_n):
     ssum = field.fr_raw_array([(x + y) % B.R for x, y in zip(s0, s1)])
     assert field.g1_from_mont_array(srs.msm(ssum, mont=False))[0] == B.g1_add(res[0], res[1])
     srs.close()
+
+
+def test_srs_upload_from_compressed_points(ctx):
+    """ark-serialize compressed G1 (the on-disk form of the reference's SRS / key files,
+    src/parameters.rs:557-592): decompression on the device reproduces the points, including
+    infinity and both y signs; a non-curve x is rejected."""
+    from oracle.transcript import g1_compressed
+    rng = random.Random(8)
+    pts = [B.g1_mul(B.G1_GEN, rng.randrange(B.R)) for _ in range(20)] + [None, B.G1_GEN, B.g1_neg(B.G1_GEN)]
+    blob = b"".join(g1_compressed(p) for p in pts)
+    srs = device.Srs(ctx, compressed=blob, window_bits=5)
+    assert field.g1_from_mont_array(srs.export()) == pts
+    sc = [rng.randrange(B.R) for _ in pts]
+    assert field.g1_from_mont_array(srs.msm(field.fr_to_mont_array(sc)))[0] == omsm.msm_naive(pts, sc)
+    srs.close()
+    # x = 0 gives y^2 = 3, a quadratic non-residue mod q: not a curve point
+    assert pow(3, (B.Q - 1) // 2, B.Q) == B.Q - 1
+    with pytest.raises(_lib.CapGpuError):
+        device.Srs(ctx, compressed=bytes(32))
