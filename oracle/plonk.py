@@ -321,12 +321,12 @@ def lin_poly(k, n, sel_polys, sigma_last, z_poly, split, wires_evals, sigma_evs,
 
 
 # ----------------------------------------------------------------------------- verifier
-def verify(vk, pub, proof, tau, ext_msg: bytes | None = None) -> bool:
-    """PLONK verifier restatement.  The final pairing equation
-    e(A, [tau]_2) = e(B, [1]_2) is checked in G1 as tau*A == B using the synthetic SRS's
-    known tau (the real reference verifier, jf-plonk ``PlonkKzgSnark::verify`` reached from
-    ``src/proof/transfer.rs:192-212``, uses the BN254 pairing; it is out of scope and stays
-    on the CPU in the reference)."""
+def verify(vk, pub, proof, tau=None, ext_msg: bytes | None = None, g2_tau=None) -> bool:
+    """PLONK verifier restatement (jf-plonk ``PlonkKzgSnark::verify`` reached from
+    ``src/proof/transfer.rs:192-212``; out of scope for the GPU and CPU-only in the reference).
+    The final equation e(A, [tau]_2) = e(B, [1]_2) is checked either with the BN254 pairing
+    (``g2_tau`` = [tau]_2, the way the reference does it; oracle/pairing.py) or, faster, in G1
+    as tau*A == B using the synthetic SRS's known ``tau``."""
     n = vk["domain_size"]
     log_n = n.bit_length() - 1
     omega = fr_root_of_unity(log_n)
@@ -391,4 +391,7 @@ def verify(vk, pub, proof, tau, ext_msg: bytes | None = None) -> bool:
     B = g1_add(g1_mul(proof["opening_proof"], zeta), g1_mul(proof["shifted_opening_proof"], u * zeta_w % R))
     B = g1_add(B, F)
     B = g1_add(B, g1_neg(g1_mul(G1_GEN, E)))
+    if g2_tau is not None:
+        from .pairing import G2_GEN, pairing_product_is_one
+        return pairing_product_is_one([(A, g2_tau), (g1_neg(B), G2_GEN)])
     return g1_mul(A, tau) == B

@@ -184,6 +184,10 @@ def test_transfer_shape_proofs_are_accepted(ctx):
         proof = plonk.PlonkKzgSnark.prove(ctx, c, pk, bl, b"note")
         pub = plonk.public_input(c)
         assert oplonk.verify(pk.vk, pub, proof, TAU, ext_msg=b"note")
+        if seed is None:
+            # the reference verifier's own check: BN254 pairing equation, no trapdoor on the G1 side
+            from oracle import pairing
+            assert oplonk.verify(pk.vk, pub, proof, ext_msg=b"note", g2_tau=pairing.g2_mul(pairing.G2_GEN, TAU))
         assert plonk.PlonkKzgSnark.prove(ctx, c, pk, bl, b"note") == proof
         bad = dict(proof)
         bad["wires_evals"] = [proof["wires_evals"][1], proof["wires_evals"][0]] + proof["wires_evals"][2:]
