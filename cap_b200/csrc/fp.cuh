@@ -10,6 +10,13 @@
 // limb alignment) so that every mad.lo.cc/madc.hi.cc pair lowers to one IMAD.WIDE.U32 with
 // carry-in/out and no separate carry-fold instructions on the ALU pipe.
 //
+// Measured on B200 (profiles/README.md): IMAD.WIDE.U32 issues at 64 lanes/clk/SM only when its
+// multiplicands sit in the operand-reuse cache; with the distinct register operands of a real
+// 8 x 8 limb product it sustains ~2.6x less, and this CIOS (half of whose multiply-adds take the
+// modulus as an immediate) tops out at ~68 G products/s with every warp slot busy.  A reduced-
+// radix variant (9 x 29-bit limbs, carry-free 64-bit column sums, 163 plain IMAD.WIDE) was
+// built, proven bit-identical and measured at 44 G products/s: slower, so it is not kept.
+//
 // All functions keep values fully reduced in [0, p): results are bit-exact canonical
 // Montgomery residues, which is what the parity tests compare.
 //

@@ -49,3 +49,4 @@ extern "C" {
 void emu_fr_inv_fermat(const uint32_t* a, uint32_t* r) { Fr x; memcpy(x.v, a, 32); Fr z = fp_inv_fermat(x); memcpy(r, z.v, 32); }
 void emu_fq_inv_fermat(const uint32_t* a, uint32_t* r) { Fq x; memcpy(x.v, a, 32); Fq z = fp_inv_fermat(x); memcpy(r, z.v, 32); }
 }
+
