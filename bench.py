@@ -320,7 +320,8 @@ def side_measurements(args, torch, ctxs, pk, srs, circ, wires_dev, wires, pubs, 
     del a, b
     n17 = 1 << 17
     srs17 = device.Srs(ctx, tau_mont=field.fr_to_mont_array([TAU % field.R])[0], size=n17)
-    sc = torch.randint(0, 1 << 60, (n17, 4), dtype=torch.int64, device="cuda", generator=g)
+    sc = torch.randint(-(1 << 63), (1 << 63) - 1, (n17, 4), dtype=torch.int64, device="cuda", generator=g)
+    sc[:, 3] &= (1 << 60) - 1  # uniform 252-bit canonical scalars
     res = torch.zeros(8, dtype=torch.int64, device="cuda")
     msm_ms = time_on_stream(lambda: _lib.check(lib.capgpu_msm_g1_dev(ctx.h, srs17.h, 0, c_void_p(sc.data_ptr()), n17, 1, 0, c_void_p(res.data_ptr())), ctx.h))
     # SURVEY 8(d) reference point: N = 2^17, c = 14, W = 19 -> 29.3 M field products = 3.98 G wide MADs
