@@ -166,7 +166,17 @@ def run_capgpu(args):
         for i in range(ci, args.batch, args.ctxs):
             prove_one(ci, i, on_device, proofs[ci])
 
+    batch_wptrs = [wires_pin[i % N_WITNESSES].data_ptr() for i in range(args.batch)]
+    batch_pubs = [pubs[i % N_WITNESSES] for i in range(args.batch)]
+    batch_bl = [bl[i % N_WITNESSES] for i in range(args.batch)]
+    batch_msgs = [ext] * args.batch
+
     def step(on_device: bool):
+        if not on_device:
+            # end to end through the call a host application makes: ONE capgpu_prove_batch over the
+            # step's notes (host pointers in, proofs out; worker threads live inside the library)
+            plonk.prove_batch_raw(ctxs, pk, batch_wptrs, batch_pubs, batch_bl, batch_msgs)
+            return
         futs = [pool.submit(worker, ci, on_device) for ci in range(args.ctxs)]
         for f in futs:
             f.result()
@@ -273,7 +283,11 @@ def side_measurements(args, torch, ctxs, pk, srs, circ, wires_dev, wires, pubs, 
     out["roofline"] = {
         "kernel": "msm_accumulate (Pippenger bucket accumulation, XYZZ mixed adds)",
         "bound": "imad", "achieved": achieved, "peak": imad_peak, "unit": "G IMAD.WIDE lane-ops/s",
-        "frac": achieved / imad_peak if imad_peak else None, "traffic": None,
+        "frac": achieved / imad_peak if imad_peak else None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of the batch-of-5 launch (2.62 M additions) in the
+        # committed capture profiles/r1_ncu_acc_reg.csv; algorithmic gather traffic of that launch is
+        # 2.62 M x 64 B = 168 MB, served mostly from L2 (the 33 MB window-shifted table is L2 resident)
+        "traffic": 48.16e6, "traffic_source": "profiles/r1_ncu_acc_reg.csv (ncu --set full, batch-of-5 launch)",
         "peak_source": "measured in this run by capgpu_calibrate (integer multiply-add issue rate; MEASURED_PEAKS.json has no INT32 figure)",
         "fmul_microbench_gmul_per_s": calib["gfmul_per_s"],
         "frac_of_fmul_microbench": (madds_per_launch * MADD_F_MULS / sec_per_launch * 1e-9 / calib["gfmul_per_s"]) if sec_per_launch > 0 else None,

@@ -19,7 +19,7 @@ EXPORTS = [
     "capgpu_ntt", "capgpu_pk_upload", "capgpu_preprocess", "capgpu_pk_export", "capgpu_pk_destroy",
     "capgpu_prove", "capgpu_job_begin", "capgpu_job_round1", "capgpu_job_round2", "capgpu_job_round3",
     "capgpu_job_round4", "capgpu_job_round5", "capgpu_job_end", "capgpu_debug_read", "capgpu_launch_count",
-    "capgpu_calibrate", "capgpu_prove_dev", "capgpu_profile_enable", "capgpu_profile_read", "capgpu_ctx_set_latency_mode", "capgpu_g1_sum_dev", "capgpu_srs_upload_compressed",
+    "capgpu_calibrate", "capgpu_prove_dev", "capgpu_profile_enable", "capgpu_profile_read", "capgpu_ctx_set_latency_mode", "capgpu_g1_sum_dev", "capgpu_srs_upload_compressed", "capgpu_prove_batch",
 ]
 
 
@@ -85,6 +85,7 @@ def load() -> ctypes.CDLL:
         "capgpu_prove_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, POINTER(Proof)]),
         "capgpu_profile_enable": (c_int, [c_void_p, c_int]),
         "capgpu_profile_read": (c_int, [c_void_p, c_int, POINTER(c_double), POINTER(c_uint64), POINTER(c_double)]),
+        "capgpu_prove_batch": (c_int, [c_void_p, c_size_t, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
         "capgpu_job_begin": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_void_p)]),
         "capgpu_job_round1": (c_int, [c_void_p, c_void_p, c_void_p]),
         "capgpu_job_round2": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

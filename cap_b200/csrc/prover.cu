@@ -6,6 +6,8 @@
 // commitments / 32-byte evaluations.  [UPSTREAM-RECALL: round structure per SURVEY.md App. A.]
 #include <string.h>
 
+#include <atomic>
+#include <thread>
 #include <vector>
 
 #include "poly.cuh"
@@ -493,6 +495,39 @@ static int prove_impl(capgpu_ctx* ctx, const capgpu_pk* pk, const uint64_t* wire
     memcpy(out->opening_proof, open2, 64);
     memcpy(out->shifted_opening_proof, open2 + 8, 64);
   });
+}
+
+// Batch of independent notes over one proving key: the B200 counterpart of the reference's rayon
+// loop over builders (/root/reference/src/utils/params_builder.rs:195-233).  One worker thread per
+// context pulls note indices from a shared counter; each context's stream carries one proof at a
+// time, so latency-bound kernels of one proof overlap with throughput-bound kernels of another.
+extern "C" int capgpu_prove_batch(capgpu_ctx* const* ctxs, size_t n_ctxs, const capgpu_pk* pk, size_t count,
+                                  const uint64_t* const* wires, const uint64_t* const* pub_inputs, const uint64_t* const* blinders,
+                                  const uint8_t* const* ext_msgs, const size_t* ext_msg_lens, capgpu_proof* out, int* status) {
+  if (!ctxs || !n_ctxs || !pk || (count && (!wires || !blinders || !out))) return CAPGPU_ERR_ARG;
+  for (size_t i = 0; i < n_ctxs; i++) if (!ctxs[i]) return CAPGPU_ERR_ARG;
+  std::atomic<size_t> next{0};
+  std::atomic<int> first_error{CAPGPU_OK};
+  auto worker = [&](capgpu_ctx* ctx) {
+    for (;;) {
+      size_t i = next.fetch_add(1);
+      if (i >= count) break;
+      const uint64_t* pi = pub_inputs ? pub_inputs[i] : nullptr;
+      const uint8_t* msg = ext_msgs ? ext_msgs[i] : nullptr;
+      size_t len = (ext_msgs && ext_msg_lens) ? ext_msg_lens[i] : 0;
+      int rc = capgpu_prove(ctx, pk, wires[i], pi, blinders[i], msg, len, &out[i]);
+      if (status) status[i] = rc;
+      if (rc != CAPGPU_OK) {
+        int expected = CAPGPU_OK;
+        first_error.compare_exchange_strong(expected, rc);
+      }
+    }
+  };
+  std::vector<std::thread> threads;
+  for (size_t t = 1; t < n_ctxs; t++) threads.emplace_back(worker, ctxs[t]);
+  worker(ctxs[0]);
+  for (auto& th : threads) th.join();
+  return first_error.load();
 }
 
 extern "C" int capgpu_debug_read(capgpu_ctx* ctx, int what, uint64_t* out, size_t max_elems, size_t* n_elems) {

@@ -175,6 +175,32 @@ class PlonkKzgSnark:
         return proof_to_dict(PlonkKzgSnark.prove_raw(ctx, pk, wires, pub, bl, extra_transcript_init_msg))
 
 
+def prove_batch_raw(ctxs, pk: ProvingKey, wire_ptrs, pubs, blinders, ext_msgs=None):
+    """``capgpu_prove_batch``: independent notes over one proving key, one worker thread per
+    context inside the library (the reference's rayon loop over notes,
+    /root/reference/src/utils/params_builder.rs:195-233).  ``wire_ptrs``: host addresses (ints) of
+    each note's 5 x n wire values; ``pubs`` / ``blinders``: lists of ABI-layout numpy arrays.
+    Returns (list of _lib.Proof, per-note status codes)."""
+    count = len(wire_ptrs)
+    lib = ctxs[0].lib
+    proofs = (_lib.Proof * count)()
+    status = (ctypes.c_int * count)()
+    cx = (c_void_p * len(ctxs))(*[c.h for c in ctxs])
+    wp = (c_void_p * count)(*wire_ptrs)
+    pp = (c_void_p * count)(*[p.ctypes.data if p.size else None for p in pubs])
+    bp = (c_void_p * count)(*[b.ctypes.data for b in blinders])
+    if ext_msgs is not None:
+        bufs = [ctypes.create_string_buffer(m, len(m)) if m else None for m in ext_msgs]
+        mp = (c_void_p * count)(*[ctypes.addressof(b) if b is not None else None for b in bufs])
+        ml = (c_size_t * count)(*[len(m) if m else 0 for m in ext_msgs])
+    else:
+        bufs, mp, ml = None, None, None
+    rc = lib.capgpu_prove_batch(cx, len(ctxs), pk.h, count, wp, pp, bp, mp, ml, proofs, status)
+    if rc != 0:
+        raise PlonkError(f"capgpu_prove_batch: {lib.capgpu_strerror(rc).decode()} (first failing status {rc})")
+    return list(proofs), list(status)
+
+
 def debug_read(ctx: Context, what: int, max_elems: int) -> list[int]:
     out = np.zeros((max_elems, 4), dtype=np.uint64)
     n = c_size_t()

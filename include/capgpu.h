@@ -161,6 +161,16 @@ int capgpu_prove(capgpu_ctx* ctx, const capgpu_pk* pk, const uint64_t* wires, co
 int capgpu_prove_dev(capgpu_ctx* ctx, const capgpu_pk* pk, const void* d_wires, const uint64_t* pub_inputs,
                      const uint64_t* blinders, const uint8_t* ext_msg, size_t ext_msg_len, capgpu_proof* out);
 
+/* `count` independent notes over one proving key, spread over `n_ctxs` contexts (one worker thread
+ * each, any mix of GPUs as long as `pk` lives on each context's device -- normally 8 contexts of
+ * one GPU).  The counterpart of the reference's rayon loop over notes
+ * (/root/reference/src/utils/params_builder.rs:195-233).  wires / pub_inputs / blinders / ext_msgs are
+ * arrays of `count` pointers; status (optional) receives the per-note code; the return value is the
+ * first non-zero code, or 0. */
+int capgpu_prove_batch(capgpu_ctx* const* ctxs, size_t n_ctxs, const capgpu_pk* pk, size_t count,
+                       const uint64_t* const* wires, const uint64_t* const* pub_inputs, const uint64_t* const* blinders,
+                       const uint8_t* const* ext_msgs, const size_t* ext_msg_lens, capgpu_proof* out, int* status);
+
 /* ---- round-level API ---------------------------------------------------------------------------
  * For a host that keeps its own transcript (the Rust shim calling upstream's
  * `PlonkTranscript`): challenges come from the caller, commitments / evaluations go back.  */

@@ -224,3 +224,33 @@ def test_device_resident_and_latency_mode_give_identical_proofs(ctx):
     assert bytes(out) == bytes(base)
     pk.close()
     srs.close()
+
+
+def test_prove_batch_matches_single_proofs(ctx):
+    """capgpu_prove_batch (worker thread per context inside the library) returns, note for note, the
+    proof the single-note call returns; a bad witness fails only its own slot."""
+    from cap_b200 import device
+    circ = synth.make_circuit(9, num_inputs=4, seed=2)
+    srs = plonk.PlonkKzgSnark.universal_setup(ctx, circ.n + 2, TAU)
+    pk = plonk.PlonkKzgSnark.preprocess(ctx, srs, circ)
+    ctxs = [ctx, device.Context(0), device.Context(0)]
+    circs = [circ] + [circ.with_witness(s) for s in range(1, 7)]
+    wires = [plonk.wire_values(c) for c in circs]
+    pubs = [field.fr_to_mont_array(plonk.public_input(c)) for c in circs]
+    rng = random.Random(6)
+    bls = [field.fr_raw_array(_mont([rng.randrange(B.R) for _ in range(17)])) for _ in circs]
+    msgs = [b"note-%d" % i for i in range(len(circs))]
+    proofs, status = plonk.prove_batch_raw(ctxs, pk, [w.ctypes.data for w in wires], pubs, bls, msgs)
+    assert status == [0] * len(circs)
+    for i in range(len(circs)):
+        single = plonk.PlonkKzgSnark.prove_raw(ctx, pk, wires[i], pubs[i], bls[i], msgs[i])
+        assert bytes(proofs[i]) == bytes(single)
+        assert oplonk.verify(pk.vk, plonk.public_input(circs[i]), plonk.proof_to_dict(proofs[i]), TAU, ext_msg=msgs[i])
+    bad = wires[3].copy()
+    bad[4, circ.num_inputs + 1, 0] ^= 1
+    with pytest.raises(plonk.PlonkError):
+        plonk.prove_batch_raw(ctxs, pk, [w.ctypes.data for w in wires[:3]] + [bad.ctypes.data], pubs[:4], bls[:4], msgs[:4])
+    for c in ctxs[1:]:
+        c.close()
+    pk.close()
+    srs.close()
