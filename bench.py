@@ -55,6 +55,10 @@ def parse_args():
     ap.add_argument("--batch", type=int, default=64, help="independent notes per GPU per step")
     ap.add_argument("--ctxs", type=int, default=8, help="prover contexts (host thread + CUDA stream) per GPU")
     ap.add_argument("--cpu-sample", type=int, default=2, help="proofs in the cpu_baseline sample (0 disables)")
+    ap.add_argument("--witness", default="dense", choices=["dense", "sparse"],
+                    help="dense: uniform witness (the headline workload); sparse: 45%% of gate inputs unused (zero variable), "
+                         "half of the fresh inputs boolean — closer to jf-relation gadget circuits; exercises the evaluation-form commitments")
+    ap.add_argument("--no-lagrange", action="store_true", help="commit wire polynomials from coefficients (A/B against the evaluation-form path)")
     ap.add_argument("--no-extras", action="store_true", help="skip roofline / MSM-latency / cpu_baseline side measurements")
     return ap.parse_args()
 
@@ -62,10 +66,11 @@ def parse_args():
 # --------------------------------------------------------------------------------------------
 # workload
 # --------------------------------------------------------------------------------------------
-def build_workload(name: str):
+def build_workload(name: str, witness: str = "dense"):
     from cap_b200 import field, plonk, synth
     log_n, nin = synth.NOTE_SHAPES[name]
-    circ = synth.make_circuit(log_n, num_inputs=nin, seed=7)
+    kw = {"zero_inputs": 0.45, "bool_inputs": 0.5} if witness == "sparse" else {}
+    circ = synth.make_circuit(log_n, num_inputs=nin, seed=7, **kw)
     circs = [circ] + [circ.with_witness(s) for s in range(1, N_WITNESSES)]
     wires = [plonk.wire_values(c) for c in circs]
     pubs = [field.fr_to_mont_array(plonk.public_input(c)) for c in circs]
@@ -134,13 +139,15 @@ def run_capgpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     assert world == args.gpus or world == 1, f"launched with WORLD_SIZE={world} but --gpus {args.gpus}"
 
-    circ, circs, wires, pubs, bl = build_workload(args.workload)
+    circ, circs, wires, pubs, bl = build_workload(args.workload, args.witness)
     n = circ.n
     ctxs = [device.Context(local) for _ in range(args.ctxs)]
     ctx0 = ctxs[0]
     lib = ctx0.lib
     srs = plonk.PlonkKzgSnark.universal_setup(ctx0, n + 2, TAU)
     pk = plonk.PlonkKzgSnark.preprocess(ctx0, srs, circ)
+    if args.no_lagrange:
+        pk.set_lagrange(False)
 
     # inputs: pinned host copies (e2e) and device-resident copies (value)
     wires_pin = [torch.from_numpy(w.view(np.int64)).pin_memory() for w in wires]
@@ -229,6 +236,7 @@ def run_capgpu(args):
         "config": {
             "workload": f"{args.workload}: TurboPlonk prove, domain n=2^{circ.log_n}, 5 wires, 13 selectors, {circ.num_inputs} public inputs, BN254",
             "notes_per_gpu_per_step": args.batch, "prover_ctxs_per_gpu": args.ctxs, "distinct_witnesses": N_WITNESSES,
+            "witness": args.witness, "wire_commitments": "coefficient form" if args.no_lagrange else "evaluation form (Lagrange commit key)",
             "parallelism": f"{world} x independent-note shards, no collective",
             "cache": "per-proof working set (126 MB workspace + 159 MB cached pk cosets) exceeds the 126 MB L2; no flush needed",
         },

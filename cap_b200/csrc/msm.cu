@@ -226,6 +226,9 @@ __device__ __forceinline__ G1XYZZ shfl_down_xyzz(const G1XYZZ& p, int delta, int
   return r;
 }
 
+constexpr uint32_t MSM_HEAVY = 255;  // == the population clamp of msm_scan's schedule
+__device__ inline G1XYZZ block_reduce_xyzz(G1XYZZ v, G1XYZZ* smem);
+
 template <int LPB, int MINB>
 __global__ void __launch_bounds__(128, MINB) msm_accumulate(const G1Affine* __restrict__ table, const uint32_t* __restrict__ entries,
                                                             const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ order,
@@ -236,11 +239,14 @@ __global__ void __launch_bounds__(128, MINB) msm_accumulate(const G1Affine* __re
   const size_t b = blockIdx.y;
   G1XYZZ acc = G1XYZZ::inf();
   size_t bucket = 0;
+  bool heavy = false;
   if (slot < K) {
     bucket = order[b * K + slot];
     const uint32_t* off = offsets + b * (K + 2);
     uint32_t start = off[bucket + 1], end = off[bucket + 2];
     const uint32_t* ent = entries + b * entries_stride;
+    heavy = end - start >= MSM_HEAVY;  // left to msm_accumulate_heavy
+    if (heavy) end = start;
     for (uint32_t e = start + lane; e < end; e += LPB) {
       uint32_t u = ent[e];
       G1Affine p = table[u & 0x7fffffffu];
@@ -254,7 +260,34 @@ __global__ void __launch_bounds__(128, MINB) msm_accumulate(const G1Affine* __re
       xyzz_add(acc, other);
     }
   }
-  if (slot < K && lane == 0) buckets[b * K + bucket] = acc;
+  if (slot < K && lane == 0 && !heavy) buckets[b * K + bucket] = acc;
+}
+
+// Buckets holding >= MSM_HEAVY entries (repeated scalars: the 0/1-valued cells of a witness column
+// committed in evaluation form all land in bucket 1 of window 0) get a whole CTA each instead of
+// LPB lanes.  The schedule lists them first (msm_scan clamps populations at 255), so every CTA
+// walks the schedule with a grid stride and stops at the first light bucket.
+__global__ void __launch_bounds__(128) msm_accumulate_heavy(const G1Affine* __restrict__ table, const uint32_t* __restrict__ entries,
+                                                            const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ order,
+                                                            G1XYZZ* buckets, size_t K, size_t entries_stride) {
+  __shared__ G1XYZZ smem[32];
+  const size_t b = blockIdx.y;
+  const uint32_t* off = offsets + b * (K + 2);
+  const uint32_t* ent = entries + b * entries_stride;
+  for (size_t slot = blockIdx.x; slot < K; slot += gridDim.x) {
+    const size_t bucket = order[b * K + slot];
+    const uint32_t start = off[bucket + 1], end = off[bucket + 2];
+    if (end - start < MSM_HEAVY) break;
+    G1XYZZ acc = G1XYZZ::inf();
+    for (uint32_t e = start + threadIdx.x; e < end; e += blockDim.x) {
+      uint32_t u = ent[e];
+      G1Affine p = table[u & 0x7fffffffu];
+      if (!p.is_inf()) xyzz_add_mixed(acc, p.x, p.y, (u >> 31) != 0);
+    }
+    acc = block_reduce_xyzz(acc, smem);
+    if (threadIdx.x == 0) buckets[b * K + bucket] = acc;
+    __syncthreads();
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -405,6 +438,11 @@ void msm_device(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const F
     case 16: launch_accumulate<16>(ctx, srs, entries, counts, order, buckets, es, batch); break;
     default: launch_accumulate<32>(ctx, srs, entries, counts, order, buckets, es, batch); break;
   }
+  {
+    dim3 grid((unsigned)(K < 64 ? K : 64), (unsigned)batch);
+    msm_accumulate_heavy<<<grid, 128, 0, ctx->stream>>>(srs->table, entries, counts, order, buckets, K, es);
+    CAPGPU_LAUNCH_CHECK(ctx);
+  }
   }
   // segmented reduction: L buckets per thread.  Depth is ~2L + 36 group operations and work
   // ~(K/L)(2L + 36), so a lone MSM (latency) wants a small L and a batch (throughput) a large
@@ -519,6 +557,105 @@ static int srs_create(capgpu_ctx* ctx, const uint64_t* points_xy, const uint64_t
   *out = srs;
   return CAPGPU_OK;
 }
+
+// ------------------------------------------------------------------------------------------
+// Lagrange-basis SRS: L_j = L_j(tau)·G = (1/n) sum_i omega^(-ij) P_i, i.e. the inverse
+// DFT of the first n monomial points taken in the group.  Radix-2 decimation-in-frequency over
+// XYZZ points in global memory (each butterfly multiplies by a 254-bit twiddle: double-and-add),
+// bit-reversal folded into the final affine conversion.  One-time cost per proving key.
+// Commitments of a polynomial given by its evaluations e_j on H are then sum_j e_j L_j — the same
+// group element as the coefficient-form MSM, with scalars that are zero / small wherever the
+// witness column is.
+// ------------------------------------------------------------------------------------------
+namespace capgpu {
+
+__device__ G1XYZZ xyzz_mul_scalar(const G1XYZZ& p, const Fr& k) {  // k canonical
+  G1XYZZ r = G1XYZZ::inf();
+  bool started = false;
+  for (int b = 253; b >= 0; b--) {
+    if (started) r = xyzz_dbl(r);
+    if ((k.v[b >> 5] >> (b & 31)) & 1) { xyzz_add(r, p); started = true; }
+  }
+  return r;
+}
+
+__global__ void lag_load(const G1Affine* __restrict__ pts, G1XYZZ* A, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  G1Affine p = pts[i];
+  A[i] = p.is_inf() ? G1XYZZ::inf() : xyzz_from_affine(p);
+}
+
+// one DIF stage of the inverse transform: (a, b) -> (a + b, (a - b) * omega^(-i * n/len))
+__global__ void __launch_bounds__(64) lag_stage(G1XYZZ* A, size_t n, size_t len, const Fr* __restrict__ omega_pows) {
+  size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n / 2) return;
+  const size_t half = len / 2;
+  const size_t blk = k / half, i = k % half;
+  const size_t i0 = blk * len + i, i1 = i0 + half;
+  G1XYZZ a = A[i0], b = A[i1];
+  G1XYZZ sum = a;
+  xyzz_add(sum, b);
+  b.Y = fp_neg(b.Y);
+  xyzz_add(a, b);
+  const size_t e = i * (n / len);
+  if (e != 0) a = xyzz_mul_scalar(a, fp_from_mont(omega_pows[n - e]));
+  A[i0] = sum;
+  A[i1] = a;
+}
+
+__global__ void __launch_bounds__(64) lag_finish(const G1XYZZ* __restrict__ A, unsigned log_n, Fr n_inv, G1Affine* out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >> log_n) return;
+  G1XYZZ v = xyzz_mul_scalar(A[i], fp_from_mont(n_inv));
+  size_t j = log_n ? (size_t)(__brevll((unsigned long long)i) >> (64 - log_n)) : 0;
+  out[j] = xyzz_to_affine(v);
+}
+
+// Bases of the evaluation-form wire commitment: [L_0 .. L_{n-1}, P_0, P_1, P_n, P_{n+1}] (the last
+// four carry the blinding polynomial (b0 + b1 X)(X^n - 1)).
+capgpu_srs* srs_lagrange(capgpu_ctx* ctx, const capgpu_srs* srs, unsigned log_n, const Fr* omega_pows, const Fr& n_inv) {
+  const size_t n = (size_t)1 << log_n;
+  CAPGPU_REQUIRE(srs->n >= n + 2, "SRS too small for the Lagrange commit key");
+  const size_t np = n + 4;
+  capgpu_srs* lag = new capgpu_srs();
+  G1XYZZ* A = nullptr;
+  try {
+    int c = ceil_log2(np) + 1;
+    if (c > 16) c = 16;
+    if (c < 4) c = 4;
+    lag->device = ctx->device;
+    lag->n = np;
+    lag->c = c;
+    lag->W = (255 + c - 1) / c;
+    lag->K = (size_t)1 << (c - 1);
+    CAPGPU_REQUIRE((size_t)lag->W * np < ((size_t)1 << 31), "SRS too large for 31-bit table indices");
+    CAPGPU_CUDA(cudaMalloc(&lag->table, (size_t)lag->W * np * sizeof(G1Affine)));
+    CAPGPU_CUDA(cudaMalloc(&A, n * sizeof(G1XYZZ)));
+    lag_load<<<ceil_div(n, 128), 128, 0, ctx->stream>>>(srs->table, A, n);
+    CAPGPU_LAUNCH_CHECK(ctx);
+    for (size_t len = n; len >= 2; len >>= 1) {
+      lag_stage<<<ceil_div(n / 2, 64), 64, 0, ctx->stream>>>(A, n, len, omega_pows);
+      CAPGPU_LAUNCH_CHECK(ctx);
+    }
+    lag_finish<<<ceil_div(n, 64), 64, 0, ctx->stream>>>(A, log_n, n_inv, lag->table);
+    CAPGPU_LAUNCH_CHECK(ctx);
+    CAPGPU_CUDA(cudaMemcpyAsync(lag->table + n, srs->table, 2 * sizeof(G1Affine), cudaMemcpyDeviceToDevice, ctx->stream));
+    CAPGPU_CUDA(cudaMemcpyAsync(lag->table + n + 2, srs->table + n, 2 * sizeof(G1Affine), cudaMemcpyDeviceToDevice, ctx->stream));
+    msm_precompute<<<ceil_div(np, 64), 64, 0, ctx->stream>>>(lag->table, np, lag->c, lag->W);
+    CAPGPU_LAUNCH_CHECK(ctx);
+    CAPGPU_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(A);
+  } catch (...) {
+    if (A) cudaFree(A);
+    if (lag->table) cudaFree(lag->table);
+    delete lag;
+    throw;
+  }
+  return lag;
+}
+
+}  // namespace capgpu
 
 extern "C" void capgpu_srs_destroy(capgpu_srs* srs) {
   if (!srs) return;

@@ -440,6 +440,22 @@ void fill_pi(capgpu_ctx* ctx, Fr* dst, size_t n, const Fr* pub, size_t l) {
   CAPGPU_LAUNCH_CHECK(ctx);
 }
 
+// Evaluation-form commitment of a masked wire polynomial: scalars of the bases P_0, P_1, P_n, P_{n+1}
+// appended after the n evaluations of each row: (b0 + b1 X)(X^n - 1) = -b0 - b1 X + b0 X^n + b1 X^(n+1).
+__global__ void lagrange_tail_kernel(Fr* evals, size_t stride, size_t n, BlindArgs args) {
+  int r = threadIdx.x >> 1, t = threadIdx.x & 1;
+  if (r >= args.rows_blinded) return;
+  Fr b = args.b[r * 2 + t];
+  Fr* row = evals + (size_t)r * stride + n;
+  row[t] = fp_neg(b);
+  row[2 + t] = b;
+}
+
+void lagrange_tail(capgpu_ctx* ctx, Fr* evals, size_t stride, size_t n, const BlindArgs& args) {
+  lagrange_tail_kernel<<<1, 32, 0, ctx->stream>>>(evals, stride, n, args);
+  CAPGPU_LAUNCH_CHECK(ctx);
+}
+
 void blind(capgpu_ctx* ctx, Fr* polys, size_t stride, size_t n, int nrows, int nb, const BlindArgs& args) {
   blind_kernel<<<nrows, 32, 0, ctx->stream>>>(polys, stride, n, nrows, nb, args);
   CAPGPU_LAUNCH_CHECK(ctx);

@@ -47,6 +47,7 @@ struct DivArgs {
 };
 
 void blind(capgpu_ctx* ctx, Fr* polys, size_t stride, size_t n, int nrows, int nb, const BlindArgs& args);
+void lagrange_tail(capgpu_ctx* ctx, Fr* evals, size_t stride, size_t n, const BlindArgs& args);
 void fill_pi(capgpu_ctx* ctx, Fr* dst, size_t n, const Fr* pub, size_t l);
 void grand_product(capgpu_ctx* ctx, const Fr* wires, size_t wstride, const Fr* sig_eval, const Fr* omega_pows, size_t n,
                    const GpArgs& a, Fr* num, Fr* den, Fr* cn, Fr* cd, Fr* z);

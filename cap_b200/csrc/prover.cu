@@ -30,6 +30,8 @@ struct capgpu_pk {
   unsigned log_n = 0;
   size_t n = 0, m = 0, num_inputs = 0;
   const capgpu_srs* srs = nullptr;
+  capgpu_srs* lag = nullptr;  // Lagrange-basis commit key [L_0..L_{n-1}, P_0, P_1, P_n, P_{n+1}] (owned)
+  bool use_lag = true;
   Fr *sel_coef = nullptr, *sig_coef = nullptr, *sig_eval = nullptr, *sel_coset = nullptr, *sig_coset = nullptr;
   Fr *xs = nullptr, *l1inv = nullptr, *zh_inv = nullptr, *omega_n = nullptr;
   HFr k[5];
@@ -82,13 +84,13 @@ capgpu_job* job_acquire(capgpu_ctx* ctx, const capgpu_pk* pk) {
     job->num_inputs = pk->num_inputs;
     const size_t n = job->n, m = job->m, NP = job->NP;
     job->div_tmax = (NP + 15) / 16 + 1;
-    size_t elems = 6 * n + 7 * NP + n + 7 * m + m + 5 * NP + 4 * NP + 2 * n + 2 * (n / 8 + 8) + 7 * m + 16 + 160 + 2 * job->div_tmax +
+    size_t elems = 6 * NP + 7 * NP + n + 7 * m + m + 5 * NP + 4 * NP + 2 * n + 2 * (n / 8 + 8) + 7 * m + 16 + 160 + 2 * job->div_tmax +
                    align_up(pk->num_inputs + 1, 8);
     size_t bytes = elems * sizeof(Fr) + 8 * sizeof(G1Affine) + 256;
     job->buf.reserve(bytes);
     Fr* p = job->buf.as<Fr>();
     auto take = [&](size_t cnt) { Fr* r = p; p += cnt; return r; };
-    job->wires_eval = take(6 * n);
+    job->wires_eval = take(6 * NP);  // rows of n evaluations, stride NP (tail: blinding scalars of the Lagrange commit)
     job->polys = take(7 * NP);
     job->z_eval = take(n);
     job->coset = take(7 * m);
@@ -116,11 +118,11 @@ void job_begin(capgpu_job* job, const uint64_t* wires, const uint64_t* pub_input
   capgpu_ctx* ctx = job->ctx;
   const capgpu_pk* pk = job->pk;
   const size_t n = job->n;
-  CAPGPU_CUDA(cudaMemcpyAsync(job->wires_eval, wires, 5 * n * sizeof(Fr),
-                              wires_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
+  CAPGPU_CUDA(cudaMemcpy2DAsync(job->wires_eval, job->NP * sizeof(Fr), wires, n * sizeof(Fr), n * sizeof(Fr), 5,
+                                wires_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
   if (pk->num_inputs)
     CAPGPU_CUDA(cudaMemcpyAsync(job->pub_dev, pub_inputs, pk->num_inputs * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
-  fill_pi(ctx, job->wires_eval + 5 * n, n, job->pub_dev, pk->num_inputs);
+  fill_pi(ctx, job->wires_eval + 5 * job->NP, n, job->pub_dev, pk->num_inputs);
   job->round = 1;
 }
 
@@ -137,12 +139,19 @@ void round1(capgpu_job* job, const uint64_t* blinders10, uint64_t* wire_comms) {
   const capgpu_pk* pk = job->pk;
   const size_t n = job->n, NP = job->NP;
   // 5 wire polynomials + the public-input polynomial: one batched INTT
-  ntt_device(ctx, pk->log_n, job->wires_eval, n, n, job->polys, NP, job->ntt_tmp, 6, true, false);
+  ntt_device(ctx, pk->log_n, job->wires_eval, n, NP, job->polys, NP, job->ntt_tmp, 6, true, false);
   BlindArgs ba;
   memcpy(ba.b, blinders10, 10 * sizeof(Fr));
   ba.rows_blinded = 5;
   blind(ctx, job->polys, NP, n, 6, 2, ba);
-  msm_device(ctx, pk->srs, 0, job->polys, n + 2, NP, 5, true, job->comms_dev, ctx->latency_mode);
+  if (pk->lag && pk->use_lag) {
+    // commit from the evaluations: sum_j w_j L_j + (b0 + b1 X)(X^n - 1) at tau — the same group element as
+    // the coefficient-form MSM, but zero / small witness cells cost nothing / one window
+    lagrange_tail(ctx, job->wires_eval, NP, n, ba);
+    msm_device(ctx, pk->lag, 0, job->wires_eval, n + 4, NP, 5, true, job->comms_dev, ctx->latency_mode);
+  } else {
+    msm_device(ctx, pk->srs, 0, job->polys, n + 2, NP, 5, true, job->comms_dev, ctx->latency_mode);
+  }
   read_points(job, 5, wire_comms);
   job->round = 2;
 }
@@ -158,7 +167,7 @@ void round2(capgpu_job* job, const uint64_t* beta, const uint64_t* gamma, const 
   ga.beta = to_dev(job->beta);
   ga.gamma = to_dev(job->gamma);
   for (int i = 0; i < 5; i++) ga.k[i] = to_dev(pk->k[i]);
-  grand_product(ctx, job->wires_eval, n, pk->sig_eval, pk->omega_n, n, ga, job->num, job->den, job->cn, job->cd, job->z_eval);
+  grand_product(ctx, job->wires_eval, NP, pk->sig_eval, pk->omega_n, n, ga, job->num, job->den, job->cn, job->cd, job->z_eval);
   Fr* zp = job->polys + 6 * NP;
   ntt_device(ctx, pk->log_n, job->z_eval, n, n, zp, NP, job->ntt_tmp, 1, true, false);
   BlindArgs ba;
@@ -282,6 +291,11 @@ void pk_finish(capgpu_ctx* ctx, capgpu_pk* pk) {
     ntt_device(ctx, pk->log_n + 3, pk->sel_coef + (size_t)s * n, n, n, pk->sel_coset + (size_t)s * m, m, tmp, 1, false, true);
   ntt_device(ctx, pk->log_n + 3, pk->sig_coef, n, n, pk->sig_coset, m, tmp, 5, false, true);
   CAPGPU_CUDA(cudaMemcpyAsync(pk->omega_n, domain_omega_powers(ctx, pk->log_n), n * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
+  {
+    const char* e = getenv("CAPGPU_LAGRANGE");
+    if (!(e && atoi(e) == 0) && pk->srs->n >= n + 2)
+      pk->lag = srs_lagrange(ctx, pk->srs, pk->log_n, pk->omega_n, to_dev(HFr::from_u64(n).inv()));
+  }
   HFr gen = HFr::from_limbs(kHostGen);
   coset_tables(ctx, domain_omega_powers(ctx, pk->log_n + 3), m, to_dev(gen), to_dev(HFr::from_u64(n)), pk->xs, pk->l1inv);
   HFr wm = host_omega(pk->log_n + 3);
@@ -322,6 +336,7 @@ void pk_free(capgpu_pk* pk) {
   cudaSetDevice(pk->device);
   Fr* ptrs[] = {pk->sel_coef, pk->sig_coef, pk->sig_eval, pk->sel_coset, pk->sig_coset, pk->xs, pk->l1inv, pk->zh_inv, pk->omega_n};
   for (Fr* p : ptrs) if (p) cudaFree(p);
+  if (pk->lag) capgpu_srs_destroy(pk->lag);
   delete pk;
 }
 
@@ -400,6 +415,19 @@ extern "C" int capgpu_pk_export(capgpu_ctx* ctx, const capgpu_pk* pk, uint64_t* 
 }
 
 extern "C" void capgpu_pk_destroy(capgpu_pk* pk) { pk_free(pk); }
+
+extern "C" int capgpu_pk_lagrange(capgpu_pk* pk, int enable) {
+  if (!pk) return CAPGPU_ERR_ARG;
+  if (enable && !pk->lag) return CAPGPU_ERR_STATE;
+  pk->use_lag = enable != 0;
+  return CAPGPU_OK;
+}
+
+extern "C" int capgpu_pk_lagrange_export(capgpu_ctx* ctx, const capgpu_pk* pk, uint64_t* points_xy, size_t count) {
+  if (!ctx || !pk || !points_xy) return CAPGPU_ERR_ARG;
+  if (!pk->lag) return CAPGPU_ERR_STATE;
+  return capgpu_srs_export(ctx, pk->lag, points_xy, count);
+}
 
 extern "C" int capgpu_job_begin(capgpu_ctx* ctx, const capgpu_pk* pk, const uint64_t* wires, const uint64_t* pub_inputs, capgpu_job** out) {
   if (!ctx || !pk || !wires || !out || (!pub_inputs && pk->num_inputs)) return CAPGPU_ERR_ARG;

@@ -88,6 +88,18 @@ class ProvingKey:
             }
         return self._vk
 
+    def set_lagrange(self, enable: bool):
+        """Commit wire columns from their evaluations (default when the key holds the Lagrange commit
+        key) or from coefficients."""
+        _lib.check(self.ctx.lib.capgpu_pk_lagrange(self.h, 1 if enable else 0), self.ctx.h)
+
+    def lagrange_bases(self, count: int | None = None):
+        """[L_0..L_{n-1}, P_0, P_1, P_n, P_{n+1}] as affine int tuples."""
+        count = self.n + 4 if count is None else count
+        out = np.zeros((count, 8), dtype=np.uint64)
+        _lib.check(self.ctx.lib.capgpu_pk_lagrange_export(self.ctx.h, self.h, _ptr(out), count), self.ctx.h)
+        return field.g1_from_mont_array(out)
+
     def close(self):
         if getattr(self, "h", None):
             self.ctx.lib.capgpu_pk_destroy(self.h)

@@ -58,12 +58,16 @@ def _gate_rest(s, j, w0, w1, w2, w3):
 
 
 def make_circuit(log_n: int, num_inputs: int = 27, seed: int = 1, utilization: float = 0.94,
-                 reuse: float = 0.35) -> SynthCircuit:
+                 reuse: float = 0.35, zero_inputs: float = 0.0, bool_inputs: float = 0.0) -> SynthCircuit:
     """Random satisfying circuit.  Input variables of a gate are drawn from earlier
     variables with probability ``reuse`` (creating copy-constraint cycles), outputs are
     fresh variables whose value solves the gate, so every row satisfies
         q_c + PI + sum q_lc_i w_i + q_mul0 w0 w1 + q_mul1 w2 w3 + q_ecc w0 w1 w2 w3 w4
-            + sum q_hash_i w_i^5 - q_o w4 = 0      (cap-specification.pdf 4.2.1 eq. (1))."""
+            + sum q_hash_i w_i^5 - q_o w4 = 0      (cap-specification.pdf 4.2.1 eq. (1)).
+    ``zero_inputs``: probability that an input slot is unused (wired to the constant-zero variable,
+    as in jf-relation's addition / multiplication / boolean gates, which use 1-2 of the 4 input
+    wires); ``bool_inputs``: probability that a fresh input variable is a bit (range-check and
+    scalar-decomposition witnesses).  Both default to 0 = dense uniform witness."""
     rng = random.Random(seed)
     n = 1 << log_n
     assert num_inputs < n
@@ -79,8 +83,13 @@ def make_circuit(log_n: int, num_inputs: int = 27, seed: int = 1, utilization: f
     for j in range(num_inputs, n_gates):
         ins = []
         for i in range(4):
-            if rng.random() < reuse:
+            if zero_inputs and rng.random() < zero_inputs:
+                ins.append(0)
+            elif rng.random() < reuse:
                 ins.append(rng.randrange(len(witness)))
+            elif bool_inputs and rng.random() < bool_inputs:
+                witness.append(rng.randrange(2))
+                ins.append(len(witness) - 1)
             else:
                 witness.append(rng.randrange(R))
                 ins.append(len(witness) - 1)
@@ -119,7 +128,7 @@ def _resolve_witness(c: SynthCircuit, seed: int) -> SynthCircuit:
             is_output[v] = True
     for v in range(2, len(witness)):
         if not is_output[v]:
-            witness[v] = rng.randrange(R)
+            witness[v] = rng.randrange(2) if witness[v] < 2 else rng.randrange(R)  # bits stay bits
     for j in range(c.num_inputs):
         witness[c.wire_variables[4][j]] = rng.randrange(R)
     s = c.selectors

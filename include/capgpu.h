@@ -131,6 +131,18 @@ int capgpu_preprocess(capgpu_ctx* ctx, const capgpu_srs* srs, unsigned log_n, si
 int capgpu_pk_export(capgpu_ctx* ctx, const capgpu_pk* pk, uint64_t* selectors, uint64_t* sigmas,
                      uint64_t* selector_comms_xy, uint64_t* sigma_comms_xy);
 void capgpu_pk_destroy(capgpu_pk* pk);
+/* Evaluation-form ("Lagrange basis") wire commitments.  Building a proving key also
+ * derives, once, the Lagrange commit key L_j = L_j(tau)·G (inverse DFT of the first n SRS points in
+ * the group); round 1 then commits the five wire columns straight from their evaluations
+ * `witness[wire_variables[i][j]]` — the same commitments `KZG10::commit` returns for the masked
+ * coefficient polynomials (src/proof/transfer.rs:181), but zero witness cells are skipped and
+ * boolean / small ones cost one bucket addition instead of 16.
+ * capgpu_pk_lagrange: enable != 0 turns the evaluation-form path on (CAPGPU_ERR_STATE if the key
+ * was built without the Lagrange commit key, i.e. with CAPGPU_LAGRANGE=0 in the environment),
+ * 0 commits from coefficients.  capgpu_pk_lagrange_export reads back the first `count` <= n + 4
+ * bases [L_0 .. L_{n-1}, P_0, P_1, P_n, P_{n+1}]. */
+int capgpu_pk_lagrange(capgpu_pk* pk, int enable);
+int capgpu_pk_lagrange_export(capgpu_ctx* ctx, const capgpu_pk* pk, uint64_t* points_xy, size_t count);
 
 /* ---- proof output --------------------------------------------------------------------------
  * Mirrors jf-plonk `Proof` (embedded at /root/reference/src/transfer.rs:60): 13 G1 + 10 Fr. */

@@ -145,6 +145,32 @@ def test_msm_edge_cases(ctx, window_bits):
     srs.close()
 
 
+def test_msm_skewed_scalars_use_the_heavy_bucket_path(ctx):
+    """Witness-like scalar vectors: mostly 0 / 1 / small values and a repeated constant, so a few
+    buckets hold thousands of entries (one CTA per heavy bucket) while the rest stay light."""
+    n = 1 << 13
+    srs = device.Srs(ctx, tau_mont=field.fr_to_mont_array([TAU])[0], size=n)
+    rng = random.Random(77)
+    const = rng.randrange(B.R)
+    vecs = []
+    for frac in (0.3, 0.9, 1.0):
+        sc = []
+        for _ in range(n):
+            u = rng.random()
+            if u < frac * 0.5:
+                sc.append(rng.randrange(2))
+            elif u < frac * 0.8:
+                sc.append(rng.randrange(256))
+            elif u < frac:
+                sc.append(const)
+            else:
+                sc.append(rng.randrange(B.R))
+        vecs.append(sc)
+    got = field.g1_from_mont_array(srs.msm(np.stack([field.fr_to_mont_array(v) for v in vecs])))
+    assert got == [omsm.kzg_commit_tau(v, TAU) for v in vecs]
+    srs.close()
+
+
 def test_msm_repeated_bases(ctx):
     """Buckets that receive P, P and -P exercise the doubling / cancellation branches."""
     P = B.g1_mul(B.G1_GEN, 99)

@@ -254,3 +254,55 @@ def test_prove_batch_matches_single_proofs(ctx):
         c.close()
     pk.close()
     srs.close()
+
+
+@pytest.mark.parametrize("log_n", [3, 6, 9])
+def test_lagrange_commit_key(ctx, log_n):
+    """The derived evaluation-form commit key is [L_j(tau) G] followed by P_0, P_1, P_n, P_{n+1}."""
+    circ = synth.make_circuit(log_n, num_inputs=2, seed=3)
+    n = circ.n
+    srs = plonk.PlonkKzgSnark.universal_setup(ctx, n + 2, TAU)
+    pk = plonk.PlonkKzgSnark.preprocess(ctx, srs, circ)
+    got = pk.lagrange_bases()
+    w = B.fr_root_of_unity(log_n)
+    zh_over_n = (pow(TAU, n, B.R) - 1) * B.inv(n, B.R) % B.R
+    lag = [zh_over_n * pow(w, j, B.R) % B.R * B.inv((TAU - pow(w, j, B.R)) % B.R, B.R) % B.R for j in range(n)]
+    assert sum(lag) % B.R == 1
+    idx = range(n) if n <= 64 else random.Random(1).sample(range(n), 24)
+    for j in idx:
+        assert got[j] == B.g1_mul(B.G1_GEN, lag[j]), j
+    mono = [B.g1_mul(B.G1_GEN, pow(TAU, e, B.R)) for e in (0, 1, n, n + 1)]
+    assert got[n:] == mono
+    pk.close()
+    srs.close()
+
+
+def test_lagrange_and_coefficient_commitments_agree_on_sparse_witness(ctx):
+    """Wire commitments from evaluations (zero / boolean cells skipped or single-window) equal the
+    coefficient-form KZG commitments and the oracle's proof."""
+    log_n = 10
+    circ = synth.make_circuit(log_n, num_inputs=5, seed=21, zero_inputs=0.45, bool_inputs=0.5)
+    n = circ.n
+    cells = [circ.witness[v] for col in circ.wire_variables for v in col]
+    assert sum(1 for c in cells if c < 2) > len(cells) // 3
+    srs = plonk.PlonkKzgSnark.universal_setup(ctx, n + 2, TAU)
+    pk = plonk.PlonkKzgSnark.preprocess(ctx, srs, circ)
+    opk = oplonk.preprocess(circ, tau=TAU)
+    bl = [random.Random(5).randrange(B.R) for _ in range(17)]
+    op = oplonk.prove(circ, opk, bl, tau=TAU, ext_msg=b"sparse")
+    a = plonk.PlonkKzgSnark.prove(ctx, circ, pk, _mont(bl), b"sparse")
+    pk.set_lagrange(False)
+    b = plonk.PlonkKzgSnark.prove(ctx, circ, pk, _mont(bl), b"sparse")
+    pk.set_lagrange(True)
+    assert a == b == op
+    # all-zero witness columns and zero blinders: commitments are the point at infinity
+    zero = np.zeros((5, n, 4), dtype=np.uint64)
+    bl0 = np.zeros((17, 4), dtype=np.uint64)
+    pub = field.fr_to_mont_array([0] * 5)
+    try:
+        p = plonk.proof_to_dict(plonk.PlonkKzgSnark.prove_raw(ctx, pk, zero, pub, bl0, None))
+        assert p["wires_poly_comms"] == [None] * 5
+    except plonk.PlonkError:
+        pass  # the all-zero assignment need not satisfy the random circuit (quotient degree check)
+    pk.close()
+    srs.close()
