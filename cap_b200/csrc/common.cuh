@@ -71,8 +71,6 @@ struct capgpu_ctx {
   double prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   double prof_units[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   uint64_t prof_cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  // debug view of the last job (device pointers owned by the job workspace)
-  struct capgpu_job* last_job = nullptr;
   struct capgpu_job* cached_job = nullptr;  // workspace reused across capgpu_prove calls
 };
 
