@@ -53,7 +53,7 @@ def parse_args():
     ap.add_argument("--impl", default="capgpu", choices=["capgpu", "reference"])
     ap.add_argument("--workload", default="transfer_2x2")
     ap.add_argument("--batch", type=int, default=64, help="independent notes per GPU per step")
-    ap.add_argument("--ctxs", type=int, default=8, help="prover contexts (host thread + CUDA stream) per GPU")
+    ap.add_argument("--ctxs", type=int, default=16, help="prover contexts (host thread + CUDA stream) per GPU")
     ap.add_argument("--cpu-sample", type=int, default=2, help="proofs in the cpu_baseline sample (0 disables)")
     ap.add_argument("--witness", default="dense", choices=["dense", "sparse"],
                     help="dense: uniform witness (the headline workload); sparse: 45%% of gate inputs unused (zero variable), "

@@ -517,6 +517,7 @@ static int srs_create(capgpu_ctx* ctx, const uint64_t* points_xy, const uint64_t
       c = ceil_log2(n_points) + 1;
       if (c > 16) c = 16;
       if (c < 4) c = 4;
+      if (const char* e = getenv("CAPGPU_WINDOW_BITS")) { int v = atoi(e); if (v >= 2 && v <= 16 && v < c) c = v; }
     }
     CAPGPU_REQUIRE(c >= 2 && c <= 16, "window_bits must be in [2, 16]");
     srs->device = ctx->device;
