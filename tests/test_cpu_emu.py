@@ -33,6 +33,13 @@ def test_device_field_ops(emu):
             assert _call(emu, f"emu_{pre}_mul", a, b) == a * b * mi % mod
             assert _call(emu, f"emu_{pre}_add", a, b) == (a + b) % mod
             assert _call(emu, f"emu_{pre}_sub", a, b) == (a - b) % mod
+    # dedicated squaring (doubled-tail rows): edge limbs with top bits set exercise the a_j << 1 / d_j split
+    sq_edge = edge + [(1 << 254) - 1, int("ffffffff" * 8, 16), int("80000000" * 8, 16), int("ffffffff00000000" * 4, 16),
+                      int("00000000ffffffff" * 4, 16), int("7fffffff80000001" * 4, 16)]
+    for a0 in sq_edge + [None] * 6000:
+        for mod, pre, mi in ((B.R, "fr", RI), (B.Q, "fq", QI)):
+            a = rng.randrange(mod) if a0 is None else a0 % mod
+            assert _call(emu, f"emu_{pre}_sqr", a) == a * a * mi % mod, hex(a)
     for _ in range(10):
         a = rng.randrange(1, B.R)
         am = B.to_mont(a, B.R)
