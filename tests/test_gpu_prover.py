@@ -306,3 +306,36 @@ def test_lagrange_and_coefficient_commitments_agree_on_sparse_witness(ctx):
         pass  # the all-zero assignment need not satisfy the random circuit (quotient degree check)
     pk.close()
     srs.close()
+
+
+@pytest.mark.parametrize("shape", ["mint", "transfer_2x2", "transfer_3x5", "transfer_5x5"])
+def test_note_shapes_match_the_c_restatement_at_full_size(ctx, shape):
+    """BASELINE configs 1-3 (n = 2^14 .. 2^17): key and proof from the GPU equal, byte for byte, what the C
+    restatement of the arkworks / jf-plonk algorithms computes on the CPU from the same SRS, circuit,
+    witness and blinders; the Python verifier accepts the proof."""
+    import os
+    from oracle import cpu
+    log_n, nin = synth.NOTE_SHAPES[shape]
+    circ = synth.make_circuit(log_n, num_inputs=nin, seed=11, zero_inputs=0.2, bool_inputs=0.2)
+    n = circ.n
+    threads = os.cpu_count() or 1
+    srs = plonk.PlonkKzgSnark.universal_setup(ctx, n + 2, TAU)
+    pk = plonk.PlonkKzgSnark.preprocess(ctx, srs, circ)
+    srs_xy = cpu.srs(field.fr_to_mont_array([TAU])[0], n + 3, threads)
+    assert np.array_equal(srs.export(), srs_xy)
+    sel_e = np.stack([field.fr_to_mont_array(s) for s in circ.selectors])
+    sig_e = np.stack([field.fr_to_mont_array(s) for s in plonk.sigma_evals(circ)])
+    sel, sig, sc, gc = cpu.preprocess(log_n, sel_e, sig_e, srs_xy, nthreads=threads)
+    gsel, gsig, gsc, ggc = pk.export()
+    assert np.array_equal(gsel, sel) and np.array_equal(gsig, sig)
+    assert np.array_equal(gsc, sc) and np.array_equal(ggc, gc)
+    wires = plonk.wire_values(circ)
+    pub = field.fr_to_mont_array(plonk.public_input(circ))
+    bl = field.fr_raw_array(_mont([random.Random(log_n).randrange(B.R) for _ in range(17)]))
+    rc, cp = cpu.prove(log_n, nin, sel, sig, sig_e, field.fr_to_mont_array(circ.k), srs_xy, sc, gc, wires, pub, bl, b"full-size", nthreads=threads)
+    assert rc == 0
+    gp = plonk.PlonkKzgSnark.prove_raw(ctx, pk, wires, pub, bl, b"full-size")
+    assert bytes(gp) == bytes(cp)
+    assert oplonk.verify(pk.vk, plonk.public_input(circ), plonk.proof_to_dict(gp), TAU, ext_msg=b"full-size")
+    pk.close()
+    srs.close()
