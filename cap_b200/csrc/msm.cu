@@ -232,7 +232,7 @@ __device__ inline G1XYZZ block_reduce_xyzz(G1XYZZ v, G1XYZZ* smem);
 template <int LPB, int MINB>
 __global__ void __launch_bounds__(128, MINB) msm_accumulate(const G1Affine* __restrict__ table, const uint32_t* __restrict__ entries,
                                                             const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ order,
-                                                            G1XYZZ* buckets, size_t K, size_t entries_stride) {
+                                                            G1XYZZ* buckets, size_t K, size_t entries_stride, uint32_t heavy_thr) {
   // grid = (batch, CTAs per vector): CTAs are issued in x-major order, so the fullest buckets of
   // every vector of the batch run first and the emptiest of all vectors form the tail
   const size_t gid = (size_t)blockIdx.y * blockDim.x + threadIdx.x;
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(128, MINB) msm_accumulate(const G1Affine* __re
     const uint32_t* off = offsets + b * (K + 2);
     uint32_t start = off[bucket + 1], end = off[bucket + 2];
     const uint32_t* ent = entries + b * entries_stride;
-    heavy = end - start >= MSM_HEAVY;  // left to msm_accumulate_heavy
+    heavy = end - start >= heavy_thr;  // left to msm_accumulate_heavy
     if (heavy) end = start;
     for (uint32_t e = start + lane; e < end; e += LPB) {
       uint32_t u = ent[e];
@@ -265,13 +265,16 @@ __global__ void __launch_bounds__(128, MINB) msm_accumulate(const G1Affine* __re
   if (slot < K && lane == 0 && !heavy) buckets[b * K + bucket] = acc;
 }
 
-// Buckets holding >= MSM_HEAVY entries (repeated scalars: the 0/1-valued cells of a witness column
-// committed in evaluation form all land in bucket 1 of window 0) get a whole CTA each instead of
-// LPB lanes.  The schedule lists them first (msm_scan clamps populations at 255), so every CTA
-// walks the schedule with a grid stride and stops at the first light bucket.
+// Buckets holding >= heavy_thr = max(MSM_HEAVY, 8 x the average population) entries (repeated
+// scalars: the 0/1-valued cells of a witness column committed in evaluation form all land in
+// bucket 1 of window 0) get a whole CTA each instead of LPB lanes.  The schedule lists them first
+// (msm_scan clamps populations at 255), so every CTA walks the schedule with a grid stride and
+// stops at the first light bucket.  (A window size whose top window holds only a few bits —
+// c = 10, 12 — piles n/4 .. n/16 entries on buckets 1..4; the default sizes, c = 15 / 16, leave
+// 14 bits there.  Such buckets still take one CTA each: 2^16 points at c = 12 cost 1.5 ms.)
 __global__ void __launch_bounds__(128) msm_accumulate_heavy(const G1Affine* __restrict__ table, const uint32_t* __restrict__ entries,
                                                             const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ order,
-                                                            G1XYZZ* buckets, size_t K, size_t entries_stride) {
+                                                            G1XYZZ* buckets, size_t K, size_t entries_stride, uint32_t heavy_thr) {
   __shared__ G1XYZZ smem[32];
   const size_t b = blockIdx.y;
   const uint32_t* off = offsets + b * (K + 2);
@@ -279,7 +282,8 @@ __global__ void __launch_bounds__(128) msm_accumulate_heavy(const G1Affine* __re
   for (size_t slot = blockIdx.x; slot < K; slot += gridDim.x) {
     const size_t bucket = order[b * K + slot];
     const uint32_t start = off[bucket + 1], end = off[bucket + 2];
-    if (end - start < MSM_HEAVY) break;
+    if (end - start < MSM_HEAVY) break;       // end of the schedule's ">= 255" class
+    if (end - start < heavy_thr) continue;    // (uniform per CTA) ordinary bucket of a densely filled vector
     G1XYZZ acc = G1XYZZ::inf();
     for (uint32_t e = start + threadIdx.x; e < end; e += blockDim.x) {
       uint32_t u = ent[e];
@@ -374,18 +378,18 @@ static const MsmTuning& msm_tuning() {
 
 template <int LPB, int MINB>
 static void launch_accumulate2(capgpu_ctx* ctx, const capgpu_srs* srs, const uint32_t* entries, const uint32_t* offsets,
-                               const uint32_t* order, G1XYZZ* buckets, size_t entries_stride, size_t batch) {
+                               const uint32_t* order, G1XYZZ* buckets, size_t entries_stride, size_t batch, uint32_t heavy_thr) {
   size_t threads = srs->K * LPB;
   const unsigned block = msm_tuning().acc_block;
   dim3 grid((unsigned)batch, ceil_div(threads, (size_t)block));
-  msm_accumulate<LPB, MINB><<<grid, block, 0, ctx->stream>>>(srs->table, entries, offsets, order, buckets, srs->K, entries_stride);
+  msm_accumulate<LPB, MINB><<<grid, block, 0, ctx->stream>>>(srs->table, entries, offsets, order, buckets, srs->K, entries_stride, heavy_thr);
   CAPGPU_LAUNCH_CHECK(ctx);
 }
 
 template <int LPB>
 static void launch_accumulate(capgpu_ctx* ctx, const capgpu_srs* srs, const uint32_t* entries, const uint32_t* offsets,
-                              const uint32_t* order, G1XYZZ* buckets, size_t entries_stride, size_t batch) {
-  launch_accumulate2<LPB, 4>(ctx, srs, entries, offsets, order, buckets, entries_stride, batch);
+                              const uint32_t* order, G1XYZZ* buckets, size_t entries_stride, size_t batch, uint32_t heavy_thr) {
+  launch_accumulate2<LPB, 4>(ctx, srs, entries, offsets, order, buckets, entries_stride, batch, heavy_thr);
 }
 
 void msm_device(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const Fr* scalars, size_t n, size_t stride,
@@ -432,20 +436,21 @@ void msm_device(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const F
   const size_t avg_entries = (size_t)W * n / K;
   while (lpb < 32 && batch * K * lpb * 2 <= msm_tuning().acc_threads && lpb * 2 * 8 <= avg_entries) lpb <<= 1;
   const size_t es = (size_t)W * n;
+  const uint32_t heavy_thr = (uint32_t)(8 * avg_entries > MSM_HEAVY ? 8 * avg_entries : MSM_HEAVY);
   {
   // units: upper bound on mixed additions (one per non-zero digit; zero digits have probability 2^-c)
   ProfScope prof_acc(ctx, PROF_MSM_ACCUMULATE, (double)batch * W * n);
   switch (lpb) {
-    case 1: launch_accumulate<1>(ctx, srs, entries, counts, order, buckets, es, batch); break;
-    case 2: launch_accumulate<2>(ctx, srs, entries, counts, order, buckets, es, batch); break;
-    case 4: launch_accumulate<4>(ctx, srs, entries, counts, order, buckets, es, batch); break;
-    case 8: launch_accumulate<8>(ctx, srs, entries, counts, order, buckets, es, batch); break;
-    case 16: launch_accumulate<16>(ctx, srs, entries, counts, order, buckets, es, batch); break;
-    default: launch_accumulate<32>(ctx, srs, entries, counts, order, buckets, es, batch); break;
+    case 1: launch_accumulate<1>(ctx, srs, entries, counts, order, buckets, es, batch, heavy_thr); break;
+    case 2: launch_accumulate<2>(ctx, srs, entries, counts, order, buckets, es, batch, heavy_thr); break;
+    case 4: launch_accumulate<4>(ctx, srs, entries, counts, order, buckets, es, batch, heavy_thr); break;
+    case 8: launch_accumulate<8>(ctx, srs, entries, counts, order, buckets, es, batch, heavy_thr); break;
+    case 16: launch_accumulate<16>(ctx, srs, entries, counts, order, buckets, es, batch, heavy_thr); break;
+    default: launch_accumulate<32>(ctx, srs, entries, counts, order, buckets, es, batch, heavy_thr); break;
   }
   {
     dim3 grid((unsigned)(K < 64 ? K : 64), (unsigned)batch);
-    msm_accumulate_heavy<<<grid, 128, 0, ctx->stream>>>(srs->table, entries, counts, order, buckets, K, es);
+    msm_accumulate_heavy<<<grid, 128, 0, ctx->stream>>>(srs->table, entries, counts, order, buckets, K, es, heavy_thr);
     CAPGPU_LAUNCH_CHECK(ctx);
   }
   }
@@ -517,6 +522,9 @@ static int srs_create(capgpu_ctx* ctx, const uint64_t* points_xy, const uint64_t
       c = ceil_log2(n_points) + 1;
       if (c > 16) c = 16;
       if (c < 4) c = 4;
+      // 2^12..2^14 points: a lone MSM is latency-bound (bucket chains, then the reduction), and many
+      // short buckets beat few long ones: measured 0.71 -> 0.46 ms (2^12), 0.62 -> 0.49 ms (2^13)
+      if (n_points >= ((size_t)1 << 12) && c < 15) c = 15;
       if (const char* e = getenv("CAPGPU_WINDOW_BITS")) { int v = atoi(e); if (v >= 2 && v <= 16 && v < c) c = v; }
     }
     CAPGPU_REQUIRE(c >= 2 && c <= 16, "window_bits must be in [2, 16]");
