@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(HERE, "libcapgpu.so")
 EXPORTS = [
     "capgpu_strerror", "capgpu_last_error", "capgpu_ctx_create", "capgpu_ctx_destroy", "capgpu_ctx_sync",
     "capgpu_ctx_stream", "capgpu_srs_upload", "capgpu_srs_setup", "capgpu_srs_export", "capgpu_msm_g1_dev", "capgpu_ntt_dev", "capgpu_srs_destroy", "capgpu_srs_size", "capgpu_msm_g1",
-    "capgpu_ntt", "capgpu_pk_upload", "capgpu_preprocess", "capgpu_pk_export", "capgpu_pk_destroy", "capgpu_pk_lagrange", "capgpu_pk_lagrange_export",
+    "capgpu_ntt", "capgpu_pk_upload", "capgpu_preprocess", "capgpu_pk_export", "capgpu_pk_destroy", "capgpu_pk_lagrange", "capgpu_pk_lagrange_export", "capgpu_msm_g1_adhoc",
     "capgpu_prove", "capgpu_job_begin", "capgpu_job_round1", "capgpu_job_round2", "capgpu_job_round3",
     "capgpu_job_round4", "capgpu_job_round5", "capgpu_job_end", "capgpu_debug_read", "capgpu_launch_count",
     "capgpu_calibrate", "capgpu_prove_dev", "capgpu_profile_enable", "capgpu_profile_read", "capgpu_ctx_set_latency_mode", "capgpu_g1_sum_dev", "capgpu_srs_upload_compressed", "capgpu_prove_batch",
@@ -81,6 +81,7 @@ def load() -> ctypes.CDLL:
         "capgpu_preprocess": (c_int, [c_void_p, c_void_p, c_uint, c_size_t, c_void_p, c_void_p, c_void_p, POINTER(c_void_p)]),
         "capgpu_pk_export": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
         "capgpu_pk_destroy": (None, [c_void_p]),
+        "capgpu_msm_g1_adhoc": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
         "capgpu_pk_lagrange": (c_int, [c_void_p, c_int]),
         "capgpu_pk_lagrange_export": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t]),
         "capgpu_prove": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, POINTER(Proof)]),

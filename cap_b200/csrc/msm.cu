@@ -701,6 +701,21 @@ extern "C" int capgpu_msm_g1_dev(capgpu_ctx* ctx, const capgpu_srs* srs, size_t 
   });
 }
 
+// MSM over bases that are not a resident SRS (the verifier's aggregated commitment sums,
+// /root/reference/src/lib.rs:517 txn_batch_verify -> PlonkKzgSnark::batch_verify): builds the
+// window-shifted tables for this one call, runs the same pipeline, frees them.
+extern "C" int capgpu_msm_g1_adhoc(capgpu_ctx* ctx, const uint64_t* points_xy, const uint64_t* scalars, size_t n, int scalars_mont,
+                                   uint64_t* out_xy) {
+  if (!ctx || !out_xy || ((!points_xy || !scalars) && n)) return CAPGPU_ERR_ARG;
+  if (n == 0) { memset(out_xy, 0, 64); return CAPGPU_OK; }
+  capgpu_srs* tmp = nullptr;
+  int rc = srs_create(ctx, points_xy, nullptr, nullptr, n, 0, &tmp);
+  if (rc != CAPGPU_OK) return rc;
+  rc = capgpu_msm_g1(ctx, tmp, 0, scalars, n, 1, scalars_mont, out_xy);
+  capgpu_srs_destroy(tmp);
+  return rc;
+}
+
 // ------------------------------------------------------------------------------------------
 // Sum of a few affine points (the fold of a point-range-split MSM: every GPU contributes the
 // 64-byte result of its slice, gathered over NVLink; EC addition is not an NCCL reduction op,

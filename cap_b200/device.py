@@ -130,3 +130,15 @@ class Srs:
         out = np.zeros((batch, 8), dtype=np.uint64)
         _lib.check(self.lib.capgpu_msm_g1(ctx.h, self.h, base_off, _ptr(a), n, batch, int(mont), _ptr(out)), ctx.h)
         return out[0] if single else out
+
+
+def msm_adhoc(ctx: Context, points_xy, scalars, mont: bool = True) -> np.ndarray:
+    """``capgpu_msm_g1_adhoc``: sum_i scalars[i] * points[i] over caller-supplied affine points
+    ((n, 8) Montgomery x||y) -- the G1 sums of the batched verifier.  Returns (8,) affine x||y."""
+    p = np.ascontiguousarray(points_xy, dtype=np.uint64)
+    a = np.ascontiguousarray(scalars, dtype=np.uint64)
+    assert p.shape[0] == a.shape[0]
+    out = np.zeros(8, dtype=np.uint64)
+    _lib.check(ctx.lib.capgpu_msm_g1_adhoc(ctx.h, _ptr(p), _ptr(a), p.shape[0], int(mont), _ptr(out)), ctx.h)
+    return out
+

@@ -96,6 +96,14 @@ int capgpu_msm_g1(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const
 int capgpu_msm_g1_dev(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const void* d_scalars, size_t n,
                       size_t batch, int scalars_mont, void* d_out_xy);
 
+/* MSM over bases that are not a resident SRS: sum_i scalars[i] * points[i] for n affine points
+ * given by the caller (x || y Montgomery, all-zero = infinity).  This is the G1 work of the
+ * batched verifier (`txn_batch_verify`, /root/reference/src/lib.rs:517, benches/batch_verification.rs:
+ * two aggregated sums over the proofs' and verifying keys' commitments); the pairings stay on the
+ * CPU.  Tables are built for the call and released. */
+int capgpu_msm_g1_adhoc(capgpu_ctx* ctx, const uint64_t* points_xy, const uint64_t* scalars, size_t n,
+                        int scalars_mont, uint64_t* out_xy);
+
 /* Sum of `count` affine points resident on the device (asynchronous on the ctx stream).  Used to
  * fold a point-range-split MSM: each GPU runs capgpu_msm_g1_dev over its slice of the bases, the
  * 64-byte partial results are gathered over NVLink (NCCL all-gather) and added here. */

@@ -321,12 +321,12 @@ def lin_poly(k, n, sel_polys, sigma_last, z_poly, split, wires_evals, sigma_evs,
 
 
 # ----------------------------------------------------------------------------- verifier
-def verify(vk, pub, proof, tau=None, ext_msg: bytes | None = None, g2_tau=None) -> bool:
-    """PLONK verifier restatement (jf-plonk ``PlonkKzgSnark::verify`` reached from
-    ``src/proof/transfer.rs:192-212``; out of scope for the GPU and CPU-only in the reference).
-    The final equation e(A, [tau]_2) = e(B, [1]_2) is checked either with the BN254 pairing
-    (``g2_tau`` = [tau]_2, the way the reference does it; oracle/pairing.py) or, faster, in G1
-    as tau*A == B using the synthetic SRS's known ``tau``."""
+def pcs_terms(vk, pub, proof, ext_msg: bytes | None = None):
+    """The verifier's work up to the pairing check, as two multi-scalar sums over commitments:
+    returns (A_terms, B_terms), lists of (G1 point, scalar), with the proof valid iff
+    e(sum A, [tau]_2) = e(sum B, [1]_2).  (jf-plonk ``Verifier::prepare_pcs_info`` +
+    ``aggregate_*``, reached from ``src/proof/transfer.rs:192-212`` and, batched, from
+    ``src/lib.rs:517``; CPU-only in the reference.)"""
     n = vk["domain_size"]
     log_n = n.bit_length() - 1
     omega = fr_root_of_unity(log_n)
@@ -364,34 +364,69 @@ def verify(vk, pub, proof, tau=None, ext_msg: bytes | None = None, g2_tau=None) 
     tmp = tmp * ((w[4] + gamma) % R) % R
     lin_eval = (-pi_eval + tmp + alpha * alpha % R * l1) % R
 
-    # [lin] from commitments
-    lin_comm = None
-    for c, s in zip(vk["selector_comms"], sel):
-        lin_comm = g1_add(lin_comm, g1_mul(c, s))
-    lin_comm = g1_add(lin_comm, g1_mul(proof["prod_perm_poly_comm"], cz))
-    lin_comm = g1_add(lin_comm, g1_mul(vk["sigma_comms"][NUM_WIRES - 1], cs))
-    for c, s in zip(proof["split_quot_poly_comms"], ct):
-        lin_comm = g1_add(lin_comm, g1_mul(c, s))
-
-    # batched opening at zeta
-    comms = [lin_comm] + proof["wires_poly_comms"] + vk["sigma_comms"][:NUM_WIRES - 1]
-    evals = [lin_eval] + w + se
-    F = None
-    E = 0
-    c = 1
-    for cm, ev in zip(comms, evals):
-        F = g1_add(F, g1_mul(cm, c))
+    # [lin] from commitments (coefficient 1 in the batched opening), then wires and sigmas with powers of v
+    B_terms = [(c, s) for c, s in zip(vk["selector_comms"], sel)]
+    B_terms.append((proof["prod_perm_poly_comm"], (cz + u) % R))  # z also opens at zeta*omega (weight u)
+    B_terms.append((vk["sigma_comms"][NUM_WIRES - 1], cs))
+    B_terms += [(c, s) for c, s in zip(proof["split_quot_poly_comms"], ct)]
+    E = lin_eval
+    c = v
+    for cm, ev in zip(proof["wires_poly_comms"] + vk["sigma_comms"][:NUM_WIRES - 1], w + se):
+        B_terms.append((cm, c))
         E = (E + c * ev) % R
         c = c * v % R
-    # combine with the shifted opening using u
-    zeta_w = zeta * omega % R
-    F = g1_add(F, g1_mul(proof["prod_perm_poly_comm"], u))
     E = (E + u * zw) % R
-    A = g1_add(proof["opening_proof"], g1_mul(proof["shifted_opening_proof"], u))
-    B = g1_add(g1_mul(proof["opening_proof"], zeta), g1_mul(proof["shifted_opening_proof"], u * zeta_w % R))
-    B = g1_add(B, F)
-    B = g1_add(B, g1_neg(g1_mul(G1_GEN, E)))
+    zeta_w = zeta * omega % R
+    B_terms.append((proof["opening_proof"], zeta))
+    B_terms.append((proof["shifted_opening_proof"], u * zeta_w % R))
+    B_terms.append((G1_GEN, (-E) % R))
+    A_terms = [(proof["opening_proof"], 1), (proof["shifted_opening_proof"], u)]
+    return A_terms, B_terms
+
+
+def _msm_terms(terms):
+    acc = None
+    for p, s in terms:
+        acc = g1_add(acc, g1_mul(p, s % R))
+    return acc
+
+
+def _check_pairing(A, B, tau, g2_tau) -> bool:
     if g2_tau is not None:
         from .pairing import G2_GEN, pairing_product_is_one
         return pairing_product_is_one([(A, g2_tau), (g1_neg(B), G2_GEN)])
     return g1_mul(A, tau) == B
+
+
+def verify(vk, pub, proof, tau=None, ext_msg: bytes | None = None, g2_tau=None) -> bool:
+    """PLONK verifier restatement (jf-plonk ``PlonkKzgSnark::verify`` reached from
+    ``src/proof/transfer.rs:192-212``; out of scope for the GPU and CPU-only in the reference).
+    The final equation e(A, [tau]_2) = e(B, [1]_2) is checked either with the BN254 pairing
+    (``g2_tau`` = [tau]_2, the way the reference does it; oracle/pairing.py) or, faster, in G1
+    as tau*A == B using the synthetic SRS's known ``tau``."""
+    A_terms, B_terms = pcs_terms(vk, pub, proof, ext_msg)
+    return _check_pairing(_msm_terms(A_terms), _msm_terms(B_terms), tau, g2_tau)
+
+
+def batch_verify_terms(instances, rs):
+    """Random-linear-combination batching of several proofs (``PlonkKzgSnark::batch_verify`` as
+    called by ``txn_batch_verify``, ``src/lib.rs:517``): instance i = (vk, pub, proof, ext_msg) is
+    weighted by rs[i]; scalars of a base shared between instances (the selector / sigma
+    commitments of a common verifying key, the generator) are merged, so the two returned
+    multi-scalar sums have ~18 + 13 k and 2 k terms for k proofs of one note type.  The batch is
+    valid iff e(sum A, [tau]_2) = e(sum B, [1]_2).  How upstream derives the weights (transcript
+    or RNG) does not change the sums' structure; the caller supplies them."""
+    A_map, B_map = {}, {}
+    for (vk, pub, proof, msg), r in zip(instances, rs):
+        A_terms, B_terms = pcs_terms(vk, pub, proof, msg)
+        for m, terms in ((A_map, A_terms), (B_map, B_terms)):
+            for p, s in terms:
+                if p is None:
+                    continue
+                m[p] = (m.get(p, 0) + r * s) % R
+    return list(A_map.items()), list(B_map.items())
+
+
+def batch_verify(instances, rs, tau=None, g2_tau=None) -> bool:
+    A_terms, B_terms = batch_verify_terms(instances, rs)
+    return _check_pairing(_msm_terms(A_terms), _msm_terms(B_terms), tau, g2_tau)

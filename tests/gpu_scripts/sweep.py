@@ -80,5 +80,22 @@ for log_n in range(12, 19):
                        "algorithmic_gbs": gbs, "gbutterflies_per_s": (n / 2) * log_n / (ms * 1e-3) * 1e-9})
     print("ntt", out["ntt"][-1], flush=True)
 
+# batch-verification shape (benches/batch_verification.rs): the aggregated commitment sum of 1024
+# proofs of one note type is ~18 + 13 * 1024 + 1 ad-hoc bases; host buffers in, affine point out
+from cap_b200.device import msm_adhoc  # noqa: E402
+n = 18 + 13 * 1024 + 1
+srs = device.Srs(ctx, tau_mont=field.fr_to_mont_array([TAU])[0], size=n)
+pts = srs.export()
+srs.close()
+host_sc = np.random.default_rng(5).integers(0, 1 << 62, size=(n, 4), dtype=np.uint64)
+host_sc[:, 3] &= (1 << 60) - 1
+got = msm_adhoc(ctx, pts, host_sc, mont=False)
+gms = cpu_time(lambda: msm_adhoc(ctx, pts, host_sc, mont=False), reps=5)
+cpu_res = cpu.msm(pts, host_sc, mont=False, nthreads=threads)
+cms = cpu_time(lambda: cpu.msm(pts, host_sc, mont=False, nthreads=threads))
+out["adhoc_msm_batch_verify_1024"] = {"points": n, "gpu_ms_host_to_host": gms, "cpu_ms": cms, "speedup": cms / gms,
+                                      "bit_exact_vs_cpu": bool(np.array_equal(cpu_res, got))}
+print("adhoc", out["adhoc_msm_batch_verify_1024"], flush=True)
+
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/sweep.json", "w"), indent=1)

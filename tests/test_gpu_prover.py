@@ -339,3 +339,47 @@ def test_note_shapes_match_the_c_restatement_at_full_size(ctx, shape):
     assert oplonk.verify(pk.vk, plonk.public_input(circ), plonk.proof_to_dict(gp), TAU, ext_msg=b"full-size")
     pk.close()
     srs.close()
+
+
+def test_batch_verification_sums_on_the_gpu(ctx):
+    """The batched verifier's two aggregated commitment sums (txn_batch_verify,
+    /root/reference/src/lib.rs:517) computed by capgpu_msm_g1_adhoc over GPU-made proofs of two
+    note types equal the oracle's, and the batch passes / fails the final check accordingly."""
+    from cap_b200 import device
+    rng = random.Random(41)
+    inst = []
+    keys = []
+    for log_n, nin, seed in ((9, 6, 1), (8, 3, 2)):
+        circ = synth.make_circuit(log_n, num_inputs=nin, seed=seed)
+        srs = plonk.PlonkKzgSnark.universal_setup(ctx, circ.n + 2, TAU)
+        pk = plonk.PlonkKzgSnark.preprocess(ctx, srs, circ)
+        keys.append((srs, pk))
+        for k in range(3):
+            c = circ if k == 0 else circ.with_witness(k)
+            msg = b"batch-%d-%d" % (log_n, k)
+            proof = plonk.PlonkKzgSnark.prove(ctx, c, pk, _mont([rng.randrange(B.R) for _ in range(17)]), msg)
+            inst.append((pk.vk, plonk.public_input(c), proof, msg))
+    rs = [1] + [rng.randrange(1, B.R) for _ in inst[1:]]
+
+    def gpu_sum(terms):
+        pts = field.g1_to_mont_array([p for p, _ in terms])
+        return field.g1_from_mont_array(device.msm_adhoc(ctx, pts, field.fr_to_mont_array([s for _, s in terms])))[0]
+
+    A_terms, B_terms = oplonk.batch_verify_terms(inst, rs)
+    A, Bsum = gpu_sum(A_terms), gpu_sum(B_terms)
+    assert A == oplonk._msm_terms(A_terms) and Bsum == oplonk._msm_terms(B_terms)
+    assert B.g1_mul(A, TAU) == Bsum
+    assert oplonk.batch_verify(inst, rs, tau=TAU)
+    bad = list(inst)
+    vk, pub, proof, msg = bad[4]
+    bad[4] = (vk, pub, dict(proof, perm_next_eval=(proof["perm_next_eval"] + 1) % B.R), msg)
+    A_terms, B_terms = oplonk.batch_verify_terms(bad, rs)
+    assert B.g1_mul(gpu_sum(A_terms), TAU) != gpu_sum(B_terms)
+    # edge cases of the ad-hoc entry point: infinity bases, zero scalars, a single term
+    P = B.g1_mul(B.G1_GEN, 5)
+    pts = field.g1_to_mont_array([P, None, P])
+    assert field.g1_from_mont_array(device.msm_adhoc(ctx, pts, field.fr_to_mont_array([3, 9, 0])))[0] == B.g1_mul(P, 3)
+    assert field.g1_from_mont_array(device.msm_adhoc(ctx, pts[:1], field.fr_to_mont_array([B.R - 1])))[0] == B.g1_neg(P)
+    for srs, pk in keys:
+        pk.close()
+        srs.close()

@@ -129,3 +129,31 @@ def test_golden_proof(golden):
     assert [hex(v) for v in proof["wires_evals"]] == gp["wires_evals"]
     assert [hex(v) for v in proof["wire_sigma_evals"]] == gp["wire_sigma_evals"]
     assert hex(proof["perm_next_eval"]) == gp["perm_next_eval"]
+
+
+def test_batch_verification_accepts_valid_batches_and_rejects_one_bad_proof(small):
+    """Batched check in the style of /root/reference/src/lib.rs:732-820 (txn_batch_verify over
+    several notes, including notes of a second circuit): two multi-scalar sums and one pairing
+    equation for the whole batch."""
+    circ, pk = small
+    circ2 = synth.make_circuit(4, num_inputs=2, seed=9)
+    pk2 = plonk.preprocess(circ2, tau=TAU)
+    rng = random.Random(31)
+    inst = []
+    for k, (c, key) in enumerate([(circ, pk), (circ.with_witness(3), pk), (circ2, pk2), (circ.with_witness(4), pk)]):
+        msg = b"note-%d" % k
+        proof = plonk.prove(c, key, [rng.randrange(B.R) for _ in range(17)], tau=TAU, ext_msg=msg)
+        inst.append((key["vk"], plonk.public_input(c), proof, msg))
+    rs = [1] + [rng.randrange(1, B.R) for _ in inst[1:]]
+    assert plonk.batch_verify(inst, rs, tau=TAU)
+    A_terms, B_terms = plonk.batch_verify_terms(inst, rs)
+    # bases shared by the three proofs of the first key are merged: 18 vk comms + generator once
+    assert len(A_terms) == 2 * len(inst)
+    assert len(B_terms) == (18 + 13) * 2 + 13 * 2 + 1
+    bad = list(inst)
+    vk, pub, proof, msg = bad[2]
+    bad[2] = (vk, [(pub[0] + 1) % B.R] + pub[1:], proof, msg)
+    assert not plonk.batch_verify(bad, rs, tau=TAU)
+    # each proof alone still verifies / fails as expected
+    assert all(plonk.verify(v, p, pr, TAU, ext_msg=m) for v, p, pr, m in inst)
+    assert not plonk.verify(*bad[2][:3], TAU, ext_msg=bad[2][3])
