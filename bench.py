@@ -293,9 +293,9 @@ def side_measurements(args, torch, ctxs, pk, srs, circ, wires_dev, wires, pubs, 
         "bound": "imad", "achieved": achieved, "peak": imad_peak, "unit": "G IMAD.WIDE lane-ops/s",
         "frac": achieved / imad_peak if imad_peak else None,
         # dram__bytes_read.sum + dram__bytes_write.sum of the batch-of-5 launch (2.62 M additions) in the
-        # committed capture profiles/r1_ncu_acc_reg.csv; algorithmic gather traffic of that launch is
-        # 2.62 M x 64 B = 168 MB, served mostly from L2 (the 33 MB window-shifted table is L2 resident)
-        "traffic": 46.55e6, "traffic_source": "profiles/r1_ncu_full_final_raw.csv (ncu --set full, batch-of-5 launch: 42.8 MB read + 3.7 MB written; the 33 MB window table stays in L2, the 116 MB of algorithmic gathers mostly hit it)",
+        # committed capture profiles/r1_ncu_full_final_raw.csv; algorithmic gather traffic of that launch is
+        # 2.62 M x 68 B = 178 MB, served mostly from L2 (the 33 MB window-shifted table is L2 resident)
+        "traffic": 46.55e6, "traffic_source": "profiles/r1_ncu_full_final_raw.csv (ncu --set full, batch-of-5 launch: 42.8 MB read + 3.7 MB written; the 33 MB window table stays in L2, the 178 MB of algorithmic gathers mostly hit it)",
         "peak_source": "measured in this run by capgpu_calibrate (integer multiply-add issue rate; MEASURED_PEAKS.json has no INT32 figure)",
         "fmul_microbench_gmul_per_s": calib["gfmul_per_s"],
         "frac_of_fmul_microbench": (madds_per_launch * MADD_F_MULS / sec_per_launch * 1e-9 / calib["gfmul_per_s"]) if sec_per_launch > 0 else None,
