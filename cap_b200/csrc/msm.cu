@@ -14,11 +14,15 @@
 //   scan     : exclusive scan of the histogram (one CTA per scalar vector).
 //   scatter  : counting-sort scatter of (table index | sign) entries by bucket.
 //   accumulate: LPB lanes per bucket walk the bucket's entries with XYZZ mixed additions
-//              (8M+2S), then a shuffle tree folds the lanes.
+//              (8M+2S), then a shuffle tree folds the lanes; buckets are scheduled fullest first
+//              and CTAs batch-interleaved; buckets far above the average population (repeated
+//              scalars) get a whole CTA each (msm_accumulate_heavy).
 //   reduce   : sum_k k*B_k by segmented running sums + small scalar multiples, CTA tree, and a
-//              final fold + conversion to affine.
+//              final fold + conversion to affine.  The low-latency schedule (lone MSMs, latency
+//              mode) uses short segments and lane-pair cooperative group operations.
 // `batch` scalar vectors over the same bases (the 5 wire / 5 split-quotient commitments of a
-// round) share every launch (grid.y = vector index).
+// round) share every launch.  Also here: SRS upload paths (affine, compressed, synthetic tau),
+// the Lagrange commit key (group inverse DFT) and the ad-hoc-bases entry point.
 #include "common.cuh"
 #include <stdlib.h>
 #include <string.h>
