@@ -157,3 +157,30 @@ def test_batch_verification_accepts_valid_batches_and_rejects_one_bad_proof(smal
     # each proof alone still verifies / fails as expected
     assert all(plonk.verify(v, p, pr, TAU, ext_msg=m) for v, p, pr, m in inst)
     assert not plonk.verify(*bad[2][:3], TAU, ext_msg=bad[2][3])
+
+
+def test_evaluation_form_commitment_identity():
+    """What the GPU's Lagrange commit key relies on: for a masked wire polynomial
+    w(X) + (b0 + b1 X)(X^n - 1), sum_j w_j L_j(tau) - b0 - b1 tau + b0 tau^n + b1 tau^(n+1) equals
+    its evaluation at tau, so committing from evaluations gives KZG10::commit's group element; and a
+    gadget-like witness (unused inputs wired to the zero variable, boolean inputs) still satisfies
+    the synthetic circuit."""
+    circ = synth.make_circuit(6, num_inputs=3, seed=13, zero_inputs=0.4, bool_inputs=0.5)
+    assert plonk.check_gates(circ) and plonk.check_gates(circ.with_witness(2))
+    n = circ.n
+    cells = [circ.witness[v] for col in circ.wire_variables for v in col]
+    assert sum(1 for c in cells if c < 2) > len(cells) // 3
+    w = B.fr_root_of_unity(circ.log_n)
+    zh = (pow(TAU, n, B.R) - 1) % B.R
+    lag = [zh * pow(w, j, B.R) % B.R * B.inv(n * (TAU - pow(w, j, B.R)) % B.R, B.R) % B.R for j in range(n)]
+    evals = [circ.witness[v] for v in circ.wire_variables[0]]
+    coeffs = ntt.ifft(evals, circ.log_n)
+    b0, b1 = 1234567, 7654321
+    masked = list(coeffs) + [0, 0]
+    masked[0] = (masked[0] - b0) % B.R
+    masked[1] = (masked[1] - b1) % B.R
+    masked[n] = b0
+    masked[n + 1] = b1
+    at_tau = sum(c * pow(TAU, i, B.R) for i, c in enumerate(masked)) % B.R
+    from_evals = (sum(e * l for e, l in zip(evals, lag)) - b0 - b1 * TAU + b0 * pow(TAU, n, B.R) + b1 * pow(TAU, n + 1, B.R)) % B.R
+    assert at_tau == from_evals
