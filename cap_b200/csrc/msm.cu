@@ -269,6 +269,85 @@ __global__ void __launch_bounds__(128, MINB) msm_accumulate(const G1Affine* __re
   if (slot < K && lane == 0 && !heavy) buckets[b * K + bucket] = acc;
 }
 
+// ------------------------------------------------------------------------------------------
+// Flat accumulation (low-latency schedule).  When the whole launch fits the GPU in one wave the
+// bucket-per-lane-group kernel finishes with the fullest buckets while most SMs idle (bucket
+// populations spread 40..90 around an average of 64 for a lone 2^17 MSM).  Here every thread takes
+// the same number S of consecutive SORTED ENTRIES instead, whichever buckets they belong to: a
+// bucket that lies inside one chunk is written directly, a chunk's leading / trailing part of a
+// bucket that continues in a neighbouring chunk goes to pfirst[t] / plast[t], and
+// msm_combine_flat adds the (typically 2-3) parts of every bucket that straddles chunks.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 4) msm_accumulate_flat(const G1Affine* __restrict__ table, const uint32_t* __restrict__ entries,
+                                                              const uint32_t* __restrict__ offsets, G1XYZZ* buckets, G1XYZZ* pfirst,
+                                                              G1XYZZ* plast, size_t K, size_t entries_stride, uint32_t S, size_t nthreads,
+                                                              uint32_t heavy_thr) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t bi = blockIdx.y;
+  const uint32_t* off = offsets + bi * (K + 2) + 1;  // off[b] .. off[b + 1] = entries of bucket b
+  const uint32_t* ent = entries + bi * entries_stride;
+  const uint32_t E = off[K];
+  const uint64_t e0l = (uint64_t)t * S;
+  if (t >= nthreads || e0l >= E) return;
+  const uint32_t e0 = (uint32_t)e0l;
+  const uint32_t e1 = e0 + S < E ? e0 + S : E;
+  // bucket of the first entry: largest b with off[b] <= e0 (skips empty buckets sharing the offset)
+  uint32_t lo = 0, hi = (uint32_t)K;
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (off[mid] <= e0) lo = mid; else hi = mid;
+  }
+  uint32_t b = lo, bs = off[b], bend = off[b + 1];
+  uint32_t run_s = e0;
+  bool skip = bend - bs >= heavy_thr;  // heavy buckets are summed by msm_accumulate_heavy
+  G1XYZZ acc = G1XYZZ::inf();
+  G1XYZZ* bk = buckets + bi * K;
+  for (uint32_t e = e0; e < e1; e++) {
+    if (e >= bend) {
+      // the run [run_s, bend) of bucket b ends inside this chunk
+      if (!skip) {
+        if (run_s == bs) bk[b] = acc;                       // whole bucket
+        else pfirst[bi * nthreads + t] = acc;               // tail of a bucket begun in an earlier chunk (run_s == e0)
+      }
+      do { b++; bs = bend; bend = off[b + 1]; } while (e >= bend);
+      run_s = e;
+      skip = bend - bs >= heavy_thr;
+      acc = G1XYZZ::inf();
+    }
+    if (!skip) {
+      uint32_t u = ent[e];
+      G1Affine p = table[u & 0x7fffffffu];
+      if (!p.is_inf()) xyzz_add_mixed(acc, p.x, p.y, (u >> 31) != 0);
+    }
+  }
+  if (!skip) {
+    if (run_s == bs && e1 == bend) bk[b] = acc;             // whole bucket ends exactly at the chunk end
+    else if (run_s == e0) pfirst[bi * nthreads + t] = acc;  // the chunk lies inside one bucket (or starts it)
+    else plast[bi * nthreads + t] = acc;                    // head of a bucket that continues in the next chunk
+  }
+}
+
+__global__ void msm_combine_flat(const uint32_t* __restrict__ offsets, G1XYZZ* buckets, const G1XYZZ* __restrict__ pfirst,
+                                 const G1XYZZ* __restrict__ plast, size_t K, uint32_t S, size_t nthreads, uint32_t heavy_thr) {
+  const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t bi = blockIdx.y;
+  if (b >= K) return;
+  const uint32_t* off = offsets + bi * (K + 2) + 1;
+  const uint32_t s = off[b], e = off[b + 1];
+  G1XYZZ* bk = buckets + bi * K;
+  if (e == s) { bk[b] = G1XYZZ::inf(); return; }
+  if (e - s >= heavy_thr) return;
+  const uint32_t ts = s / S, te = (e - 1) / S;
+  if (ts == te) return;  // written whole by msm_accumulate_flat
+  const G1XYZZ* pf = pfirst + bi * nthreads;
+  G1XYZZ acc = (s == ts * S) ? pf[ts] : plast[bi * nthreads + ts];
+  for (uint32_t t = ts + 1; t <= te; t++) {
+    G1XYZZ q = pf[t];
+    xyzz_add(acc, q);
+  }
+  bk[b] = acc;
+}
+
 // Buckets holding >= heavy_thr = max(MSM_HEAVY, 8 x the average population) entries (repeated
 // scalars: the 0/1-valued cells of a witness column committed in evaluation form all land in
 // bucket 1 of window 0) get a whole CTA each instead of LPB lanes.  The schedule lists them first
@@ -510,15 +589,17 @@ struct MsmTuning {
   size_t acc_threads;  // target thread count when choosing lanes per bucket
   unsigned acc_block;  // CTA size of msm_accumulate
   bool pair;           // lane-pair cooperative reduction in the low-latency schedule
+  bool flat;           // flat (equal chunks of entries) accumulation for one-wave launches of that schedule
 };
 
 static const MsmTuning& msm_tuning() {
   static MsmTuning t = [] {
-    MsmTuning x{0, 65536, 128, true};  // measured: a 2^17-point MSM runs 7 % faster with 2 lanes per bucket than with 4
+    MsmTuning x{0, 65536, 128, true, true};  // measured: a 2^17-point MSM runs 7 % faster with 2 lanes per bucket than with 4
     if (const char* e = getenv("CAPGPU_RED_SEG")) x.red_seg = atoi(e);
     if (const char* e = getenv("CAPGPU_ACC_THREADS")) x.acc_threads = (size_t)atol(e);
     if (const char* e = getenv("CAPGPU_ACC_BLOCK")) x.acc_block = (unsigned)atoi(e);
     if (const char* e = getenv("CAPGPU_RED_PAIR")) x.pair = atoi(e) != 0;
+    if (const char* e = getenv("CAPGPU_ACC_FLAT")) x.flat = atoi(e) != 0;
     return x;
   }();
   return t;
@@ -585,7 +666,31 @@ void msm_device(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const F
   while (lpb < 32 && batch * K * lpb * 2 <= msm_tuning().acc_threads && lpb * 2 * 8 <= avg_entries) lpb <<= 1;
   const size_t es = (size_t)W * n;
   const uint32_t heavy_thr = (uint32_t)(8 * avg_entries > MSM_HEAVY ? 8 * avg_entries : MSM_HEAVY);
-  {
+  // one-wave launches in the low-latency schedule: equal chunks of sorted entries per thread
+  const size_t wave_threads = (size_t)ctx->sm_count * 4 * 128;
+  const bool flat = latency && msm_tuning().flat && batch * K * lpb <= wave_threads && es >= 4 * wave_threads;
+  if (flat) {
+    ProfScope prof_acc(ctx, PROF_MSM_ACCUMULATE, (double)batch * W * n);
+    const size_t per_vec_threads = wave_threads / batch;
+    const uint32_t S = (uint32_t)((es + per_vec_threads - 1) / per_vec_threads);
+    const size_t nthreads = (es + S - 1) / S;
+    ctx->msm_flat.reserve(2 * batch * nthreads * sizeof(G1XYZZ));
+    G1XYZZ* pfirst = ctx->msm_flat.as<G1XYZZ>();
+    G1XYZZ* plast = pfirst + batch * nthreads;
+    {
+      dim3 grid(ceil_div(nthreads, 128), (unsigned)batch);
+      msm_accumulate_flat<<<grid, 128, 0, ctx->stream>>>(srs->table, entries, counts, buckets, pfirst, plast, K, es, S, nthreads, heavy_thr);
+      CAPGPU_LAUNCH_CHECK(ctx);
+    }
+    {
+      dim3 grid(ceil_div(K, 128), (unsigned)batch);
+      msm_combine_flat<<<grid, 128, 0, ctx->stream>>>(counts, buckets, pfirst, plast, K, S, nthreads, heavy_thr);
+      CAPGPU_LAUNCH_CHECK(ctx);
+    }
+    dim3 grid((unsigned)(K < 64 ? K : 64), (unsigned)batch);
+    msm_accumulate_heavy<<<grid, 128, 0, ctx->stream>>>(srs->table, entries, counts, order, buckets, K, es, heavy_thr);
+    CAPGPU_LAUNCH_CHECK(ctx);
+  } else {
   // units: upper bound on mixed additions (one per non-zero digit; zero digits have probability 2^-c)
   ProfScope prof_acc(ctx, PROF_MSM_ACCUMULATE, (double)batch * W * n);
   switch (lpb) {

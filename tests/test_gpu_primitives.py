@@ -145,10 +145,13 @@ def test_msm_edge_cases(ctx, window_bits):
     srs.close()
 
 
-def test_msm_skewed_scalars_use_the_heavy_bucket_path(ctx):
+@pytest.mark.parametrize("log_n", [13, 15])
+def test_msm_skewed_scalars_use_the_heavy_bucket_path(ctx, log_n):
     """Witness-like scalar vectors: mostly 0 / 1 / small values and a repeated constant, so a few
-    buckets hold thousands of entries (one CTA per heavy bucket) while the rest stay light."""
-    n = 1 << 13
+    buckets hold thousands of entries (one CTA per heavy bucket) while the rest stay light or empty.
+    At 2^15 the lone-MSM schedule takes the flat (equal chunks of sorted entries) accumulation,
+    whose chunks then start and end inside, at and across bucket boundaries."""
+    n = 1 << log_n
     srs = device.Srs(ctx, tau_mont=field.fr_to_mont_array([TAU])[0], size=n)
     rng = random.Random(77)
     const = rng.randrange(B.R)
@@ -166,8 +169,10 @@ def test_msm_skewed_scalars_use_the_heavy_bucket_path(ctx):
             else:
                 sc.append(rng.randrange(B.R))
         vecs.append(sc)
-    got = field.g1_from_mont_array(srs.msm(np.stack([field.fr_to_mont_array(v) for v in vecs])))
-    assert got == [omsm.kzg_commit_tau(v, TAU) for v in vecs]
+    exp = [omsm.kzg_commit_tau(v, TAU) for v in vecs]
+    assert field.g1_from_mont_array(srs.msm(np.stack([field.fr_to_mont_array(v) for v in vecs]))) == exp
+    for v, e in zip(vecs, exp):  # each vector alone: the lone-MSM schedule
+        assert field.g1_from_mont_array(srs.msm(field.fr_to_mont_array(v)))[0] == e
     srs.close()
 
 
