@@ -203,6 +203,17 @@ def test_msm_at_bench_sizes(ctx, log_n):
     s0, s1 = field.fr_from_raw_array(a[0]), field.fr_from_raw_array(a[1])
     ssum = field.fr_raw_array([(x + y) % B.R for x, y in zip(s0, s1)])
     assert field.g1_from_mont_array(srs.msm(ssum, mont=False))[0] == B.g1_add(res[0], res[1])
+    # lone-MSM schedule (flat accumulation + lane-pair reduction) on degenerate vectors: nothing to add,
+    # one giant bucket, a single non-zero scalar at either end
+    zeros = np.zeros((n, 4), dtype=np.uint64)
+    assert field.g1_from_mont_array(srs.msm(zeros, mont=False))[0] is None
+    ones = zeros.copy()
+    ones[:, 0] = 1
+    assert field.g1_from_mont_array(srs.msm(ones, mont=False))[0] == omsm.kzg_commit_tau([1] * n, TAU)
+    for pos in (0, n - 1):
+        one = zeros.copy()
+        one[pos] = a[0][pos]
+        assert field.g1_from_mont_array(srs.msm(one, mont=False))[0] == B.g1_mul(B.g1_mul(B.G1_GEN, pow(TAU, pos, B.R)), s0[pos])
     srs.close()
 
 

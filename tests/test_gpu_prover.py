@@ -166,6 +166,16 @@ def test_error_behaviour(ctx):
         plonk.PlonkKzgSnark.prove(ctx, bad, pk, bl)
     # the ctx stays usable afterwards
     assert plonk.PlonkKzgSnark.prove(ctx, circ, pk, bl) == good
+    # argument checking of the newer entry points: null handles / buffers are CAPGPU_ERR_ARG, never a crash
+    lib = ctx.lib
+    assert lib.capgpu_pk_lagrange(None, 1) == -2
+    assert lib.capgpu_pk_lagrange_export(ctx.h, pk.h, None, 4) == -2
+    out = np.zeros(8, dtype=np.uint64)
+    assert lib.capgpu_msm_g1_adhoc(ctx.h, None, None, 3, 1, _ptr(out)) == -2
+    assert lib.capgpu_msm_g1_adhoc(ctx.h, None, None, 0, 1, _ptr(out)) == 0 and not out.any()
+    assert lib.capgpu_prove_batch(None, 0, pk.h, 0, None, None, None, None, None, None, None) == -2
+    pts = np.zeros((pk.n + 4, 8), dtype=np.uint64)
+    assert lib.capgpu_pk_lagrange_export(ctx.h, pk.h, _ptr(pts), pk.n + 5) != 0  # more than n + 4 bases
     pk.close()
     srs.close()
 
