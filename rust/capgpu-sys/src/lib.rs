@@ -48,7 +48,30 @@ extern "C" {
     pub fn capgpu_job_round4(job: *mut capgpu_job, zeta: *const u64, evals: *mut u64) -> c_int;
     pub fn capgpu_job_round5(job: *mut capgpu_job, v: *const u64, opening_comms_xy: *mut u64) -> c_int;
     pub fn capgpu_job_end(job: *mut capgpu_job);
+
+    // scheduling, SRS variants, device-resident and batched entry points
+    pub fn capgpu_ctx_set_latency_mode(ctx: *mut capgpu_ctx, on: c_int) -> c_int;
+    pub fn capgpu_ctx_stream(ctx: *mut capgpu_ctx) -> *mut c_void;
+    pub fn capgpu_srs_upload_compressed(ctx: *mut capgpu_ctx, bytes: *const u8, n_points: usize, window_bits: c_int, out: *mut *mut capgpu_srs) -> c_int;
+    pub fn capgpu_srs_setup(ctx: *mut capgpu_ctx, tau: *const u64, n_points: usize, window_bits: c_int, out: *mut *mut capgpu_srs) -> c_int;
+    pub fn capgpu_srs_export(ctx: *mut capgpu_ctx, srs: *const capgpu_srs, points_xy: *mut u64, n_points: usize) -> c_int;
+    pub fn capgpu_srs_size(srs: *const capgpu_srs) -> usize;
+    pub fn capgpu_msm_g1_dev(ctx: *mut capgpu_ctx, srs: *const capgpu_srs, base_off: usize, d_scalars: *const c_void, n: usize, batch: usize, scalars_mont: c_int, d_out_xy: *mut c_void) -> c_int;
+    pub fn capgpu_msm_g1_adhoc(ctx: *mut capgpu_ctx, points_xy: *const u64, scalars: *const u64, n: usize, scalars_mont: c_int, out_xy: *mut u64) -> c_int;
+    pub fn capgpu_g1_sum_dev(ctx: *mut capgpu_ctx, d_points_xy: *const c_void, count: usize, d_out_xy: *mut c_void) -> c_int;
+    pub fn capgpu_ntt_dev(ctx: *mut capgpu_ctx, d_in: *const c_void, in_len: usize, d_out: *mut c_void, log_n: c_uint, batch: usize, inverse: c_int, coset: c_int) -> c_int;
+    pub fn capgpu_preprocess(ctx: *mut capgpu_ctx, srs: *const capgpu_srs, log_n: c_uint, num_inputs: usize, selector_evals: *const u64, sigma_evals: *const u64, k: *const u64, out: *mut *mut capgpu_pk) -> c_int;
+    pub fn capgpu_pk_export(ctx: *mut capgpu_ctx, pk: *const capgpu_pk, selectors: *mut u64, sigmas: *mut u64, selector_comms_xy: *mut u64, sigma_comms_xy: *mut u64) -> c_int;
+    pub fn capgpu_pk_lagrange(pk: *mut capgpu_pk, enable: c_int) -> c_int;
+    pub fn capgpu_pk_lagrange_export(ctx: *mut capgpu_ctx, pk: *const capgpu_pk, points_xy: *mut u64, count: usize) -> c_int;
+    pub fn capgpu_prove_dev(ctx: *mut capgpu_ctx, pk: *const capgpu_pk, d_wires: *const c_void, pub_inputs: *const u64, blinders: *const u64, ext_msg: *const u8, ext_msg_len: usize, out: *mut capgpu_proof) -> c_int;
+    pub fn capgpu_prove_batch(ctxs: *const *mut capgpu_ctx, n_ctxs: usize, pk: *const capgpu_pk, count: usize, wires: *const *const u64, pub_inputs: *const *const u64, blinders: *const *const u64, ext_msgs: *const *const u8, ext_msg_lens: *const usize, out: *mut capgpu_proof, status: *mut c_int) -> c_int;
+
+    // diagnostics
+    pub fn capgpu_debug_read(ctx: *mut capgpu_ctx, what: c_int, out: *mut u64, max_elems: usize, n_elems: *mut usize) -> c_int;
+    pub fn capgpu_launch_count(ctx: *const capgpu_ctx) -> u64;
+    pub fn capgpu_profile_enable(ctx: *mut capgpu_ctx, on: c_int) -> c_int;
+    pub fn capgpu_profile_read(ctx: *const capgpu_ctx, id: c_int, total_ms: *mut f64, launches: *mut u64, units: *mut f64) -> c_int;
+    pub fn capgpu_calibrate(ctx: *mut capgpu_ctx, gimad_per_s: *mut f64, gimad_wide_per_s: *mut f64, gfmul_per_s: *mut f64) -> c_int;
 }
 
-#[allow(dead_code)]
-fn _unused(_: *mut c_void) {}

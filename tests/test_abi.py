@@ -26,6 +26,13 @@ def test_library_exports_every_declared_symbol():
     assert set(_lib.EXPORTS) == set(names)
 
 
+def test_rust_sys_crate_declares_the_same_entry_points():
+    """rust/capgpu-sys (the binding INTEGRATION.md describes; unbuilt here) stays in step with the header."""
+    text = open(os.path.join(ROOT, "rust", "capgpu-sys", "src", "lib.rs")).read()
+    rust = set(re.findall(r"\bpub fn (capgpu_[a-z0-9_]+)\s*\(", text))
+    assert rust == set(_declared())
+
+
 def test_error_strings():
     lib = _lib.load()
     assert lib.capgpu_strerror(0) == b"ok"
