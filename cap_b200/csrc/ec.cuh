@@ -43,7 +43,7 @@ __host__ __device__ inline G1XYZZ xyzz_dbl(const G1XYZZ& p) {
   Fq M = fp_add(fp_dbl(XX), XX);
   G1XYZZ r;
   r.X = fp_sub(fp_sqr(M), fp_dbl(S));
-  r.Y = fp_sub(fp_mul(M, fp_sub(S, r.X)), fp_mul(W, p.Y));
+  r.Y = fp_mul_sub(M, fp_sub(S, r.X), W, p.Y);  // one reduction for the two products
   r.ZZ = fp_mul(V, p.ZZ);
   r.ZZZ = fp_mul(W, p.ZZZ);
   return r;
@@ -59,7 +59,7 @@ __host__ __device__ inline G1XYZZ xyzz_dbl_affine(const Fq& x, const Fq& y) {
   Fq M = fp_add(fp_dbl(XX), XX);
   G1XYZZ r;
   r.X = fp_sub(fp_sqr(M), fp_dbl(S));
-  r.Y = fp_sub(fp_mul(M, fp_sub(S, r.X)), fp_mul(W, y));
+  r.Y = fp_mul_sub(M, fp_sub(S, r.X), W, y);
   r.ZZ = V;
   r.ZZZ = W;
   return r;
@@ -86,7 +86,7 @@ __host__ __device__ inline void xyzz_add_mixed(G1XYZZ& acc, const Fq& x2, const 
   Fq PPP = fp_mul(P, PP);
   Fq Qq = fp_mul(acc.X, PP);
   Fq X3 = fp_sub(fp_sub(fp_sqr(Rr), PPP), fp_dbl(Qq));
-  Fq Y3 = fp_sub(fp_mul(Rr, fp_sub(Qq, X3)), fp_mul(acc.Y, PPP));
+  Fq Y3 = fp_mul_sub(Rr, fp_sub(Qq, X3), acc.Y, PPP);  // fused: 9 reductions per mixed addition instead of 10
   acc.X = X3;
   acc.Y = Y3;
   acc.ZZ = fp_mul(acc.ZZ, PP);
@@ -112,7 +112,7 @@ __host__ __device__ inline void xyzz_add(G1XYZZ& acc, const G1XYZZ& q) {
   Fq PPP = fp_mul(P, PP);
   Fq Qq = fp_mul(U1, PP);
   Fq X3 = fp_sub(fp_sub(fp_sqr(Rr), PPP), fp_dbl(Qq));
-  Fq Y3 = fp_sub(fp_mul(Rr, fp_sub(Qq, X3)), fp_mul(S1, PPP));
+  Fq Y3 = fp_mul_sub(Rr, fp_sub(Qq, X3), S1, PPP);
   acc.X = X3;
   acc.Y = Y3;
   acc.ZZ = fp_mul(fp_mul(acc.ZZ, q.ZZ), PP);

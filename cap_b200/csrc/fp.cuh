@@ -243,6 +243,64 @@ __host__ __device__ __forceinline__ Fp<PR> fp_mul(const Fp<PR>& a, const Fp<PR>&
   return r;
 }
 
+// ---- fused a*b + c*d -------------------------------------------------------------------------
+// Both products' rows go into the same accumulators before each reduction step: 8 x (16 + 8) + 8
+// wide MADs instead of 2 x 136 — one Montgomery reduction for the sum.  The sliding 9-limb window
+// still cannot overflow: after row i it holds less than 3 B^(i+1) p and p < 0.19 B^8.  The result
+// is < 1.6 p before the final conditional subtraction.  (Y3 of the curve formulas, gate sums.)
+template <class PR>
+__host__ __device__ __forceinline__ void mont_mad_row_noshift(uint32_t* X, uint32_t* Y, const uint32_t* a, uint32_t bi) {
+  // X aligned at this row's base, Y one limb higher (already shifted by the first product's row)
+  mad_wide_cc(X[0], X[1], a[0], bi);
+  madc_wide_cc(X[2], X[3], a[2], bi);
+  madc_wide_cc(X[4], X[5], a[4], bi);
+  madc_wide_cc(X[6], X[7], a[6], bi);
+  Y[7] = addc(Y[7], 0);
+  mad_wide_cc(Y[0], Y[1], a[1], bi);
+  madc_wide_cc(Y[2], Y[3], a[3], bi);
+  madc_wide_cc(Y[4], Y[5], a[5], bi);
+  madc_wide_cc(Y[6], Y[7], a[7], bi);  // no carry out: the window bound above
+}
+
+template <class PR>
+__host__ __device__ __forceinline__ Fp<PR> fp_mul_add(const Fp<PR>& a, const Fp<PR>& b, const Fp<PR>& c, const Fp<PR>& d) {
+  uint32_t E[8], O[8];
+  mul_wide(E[0], E[1], a.v[0], b.v[0]);
+  mul_wide(E[2], E[3], a.v[2], b.v[0]);
+  mul_wide(E[4], E[5], a.v[4], b.v[0]);
+  mul_wide(E[6], E[7], a.v[6], b.v[0]);
+  mul_wide(O[0], O[1], a.v[1], b.v[0]);
+  mul_wide(O[2], O[3], a.v[3], b.v[0]);
+  mul_wide(O[4], O[5], a.v[5], b.v[0]);
+  mul_wide(O[6], O[7], a.v[7], b.v[0]);
+  mont_mad_row_noshift<PR>(E, O, c.v, d.v[0]);
+  mont_reduce_step<PR>(E, O);
+#pragma unroll
+  for (int i = 1; i < 8; i += 2) {
+    mont_mad_row<PR>(O, E, a.v, b.v[i]);
+    mont_mad_row_noshift<PR>(O, E, c.v, d.v[i]);
+    mont_reduce_step<PR>(O, E);
+    if (i + 1 < 8) {
+      mont_mad_row<PR>(E, O, a.v, b.v[i + 1]);
+      mont_mad_row_noshift<PR>(E, O, c.v, d.v[i + 1]);
+      mont_reduce_step<PR>(E, O);
+    }
+  }
+  Fp<PR> r;
+  r.v[0] = add_cc(E[0], O[1]);
+#pragma unroll
+  for (int i = 1; i < 7; i++) r.v[i] = addc_cc(E[i], O[i + 1]);
+  r.v[7] = addc(E[7], 0);
+  fp_final_sub(r);
+  return r;
+}
+
+// a*b - c*d
+template <class PR>
+__host__ __device__ __forceinline__ Fp<PR> fp_mul_sub(const Fp<PR>& a, const Fp<PR>& b, const Fp<PR>& c, const Fp<PR>& d) {
+  return fp_mul_add(a, b, c, fp_neg(d));
+}
+
 // ---- Montgomery squaring --------------------------------------------------------------------
 // Same row / reduce interleaving as fp_mul, but row i multiplies a_i by the doubled tail of a
 // only:  a^2 = sum_i a_i B^i (a_i B^i + 2 sum_{j>i} a_j B^j), so row i has 8 - i products instead

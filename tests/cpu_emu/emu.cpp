@@ -9,6 +9,14 @@ using namespace capgpu;
 extern "C" {
 void emu_fr_mul(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fr x, y; memcpy(x.v, a, 32); memcpy(y.v, b, 32); Fr z = fp_mul(x, y); memcpy(r, z.v, 32); }
 void emu_fq_mul(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fq x, y; memcpy(x.v, a, 32); memcpy(y.v, b, 32); Fq z = fp_mul(x, y); memcpy(r, z.v, 32); }
+void emu_fq_mul_add(const uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* d, uint32_t* r) {
+  Fq x, y, z, w; memcpy(x.v, a, 32); memcpy(y.v, b, 32); memcpy(z.v, c, 32); memcpy(w.v, d, 32);
+  Fq o = fp_mul_add(x, y, z, w); memcpy(r, o.v, 32);
+}
+void emu_fr_mul_sub(const uint32_t* a, const uint32_t* b, const uint32_t* c, const uint32_t* d, uint32_t* r) {
+  Fr x, y, z, w; memcpy(x.v, a, 32); memcpy(y.v, b, 32); memcpy(z.v, c, 32); memcpy(w.v, d, 32);
+  Fr o = fp_mul_sub(x, y, z, w); memcpy(r, o.v, 32);
+}
 void emu_fr_sqr(const uint32_t* a, uint32_t* r) { Fr x; memcpy(x.v, a, 32); Fr z = fp_sqr(x); memcpy(r, z.v, 32); }
 void emu_fq_sqr(const uint32_t* a, uint32_t* r) { Fq x; memcpy(x.v, a, 32); Fq z = fp_sqr(x); memcpy(r, z.v, 32); }
 void emu_fr_add(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fr x, y; memcpy(x.v, a, 32); memcpy(y.v, b, 32); Fr z = fp_add(x, y); memcpy(r, z.v, 32); }

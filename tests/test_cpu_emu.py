@@ -40,6 +40,17 @@ def test_device_field_ops(emu):
         for mod, pre, mi in ((B.R, "fr", RI), (B.Q, "fq", QI)):
             a = rng.randrange(mod) if a0 is None else a0 % mod
             assert _call(emu, f"emu_{pre}_sqr", a) == a * a * mi % mod, hex(a)
+    # fused a*b + c*d / a*b - c*d (one reduction for two products): worst-case operands first
+    big = [B.Q - 1, B.Q - 2, (1 << 253) % B.Q, 0, 1]
+    quads = [(w, x, y, z) for w in big[:3] for x in big[:3] for y in big for z in big]
+    quads += [tuple(rng.randrange(B.Q) for _ in range(4)) for _ in range(4000)]
+    for w, x, y, z in quads:
+        assert _call(emu, "emu_fq_mul_add", w, x, y, z) == (w * x + y * z) * QI % B.Q
+    for _ in range(2000):
+        w, x, y, z = (rng.randrange(B.R) for _ in range(4))
+        assert _call(emu, "emu_fr_mul_sub", w, x, y, z) == (w * x - y * z) * RI % B.R
+    m = B.R - 1
+    assert _call(emu, "emu_fr_mul_sub", m, m, m, m) == 0 and _call(emu, "emu_fr_mul_sub", m, m, 0, m) == m * m * RI % B.R
     for _ in range(10):
         a = rng.randrange(1, B.R)
         am = B.to_mont(a, B.R)
