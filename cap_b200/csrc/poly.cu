@@ -167,17 +167,16 @@ __global__ void __launch_bounds__(128) quotient_kernel(const Fr* __restrict__ co
 #pragma unroll
   for (int j = 0; j < 5; j++) w[j] = coset[(size_t)j * m + i];
   // gate part
+  // the twelve selector products are summed two at a time with one Montgomery reduction per pair
   Fr acc = fp_add(sel[11 * m + i], coset[5 * m + i]);  // q_c + PI
-#pragma unroll
-  for (int j = 0; j < 4; j++) acc = fp_add(acc, fp_mul(sel[(size_t)j * m + i], w[j]));
+  acc = fp_add(acc, fp_mul_add(sel[0 * m + i], w[0], sel[1 * m + i], w[1]));
+  acc = fp_add(acc, fp_mul_add(sel[2 * m + i], w[2], sel[3 * m + i], w[3]));
   Fr w01 = fp_mul(w[0], w[1]);
   Fr w23 = fp_mul(w[2], w[3]);
-  acc = fp_add(acc, fp_mul(sel[4 * m + i], w01));
-  acc = fp_add(acc, fp_mul(sel[5 * m + i], w23));
-#pragma unroll
-  for (int j = 0; j < 4; j++) acc = fp_add(acc, fp_mul(sel[(size_t)(6 + j) * m + i], pow5(w[j])));
-  acc = fp_sub(acc, fp_mul(sel[10 * m + i], w[4]));
-  acc = fp_add(acc, fp_mul(sel[12 * m + i], fp_mul(fp_mul(w01, w23), w[4])));
+  acc = fp_add(acc, fp_mul_add(sel[4 * m + i], w01, sel[5 * m + i], w23));
+  acc = fp_add(acc, fp_mul_add(sel[6 * m + i], pow5(w[0]), sel[7 * m + i], pow5(w[1])));
+  acc = fp_add(acc, fp_mul_add(sel[8 * m + i], pow5(w[2]), sel[9 * m + i], pow5(w[3])));
+  acc = fp_add(acc, fp_mul_sub(sel[12 * m + i], fp_mul(fp_mul(w01, w23), w[4]), sel[10 * m + i], w[4]));
   // permutation part
   Fr z = coset[6 * m + i];
   size_t inext = i + 8;
@@ -193,9 +192,8 @@ __global__ void __launch_bounds__(128) quotient_kernel(const Fr* __restrict__ co
     r2 = fp_mul(r2, fp_add(wg, fp_mul(a.beta, sig[(size_t)j * m + i])));
   }
   acc = fp_add(acc, fp_mul(a.alpha, fp_sub(r1, r2)));
-  acc = fp_mul(acc, a.zh_inv[i & 7]);  // device table: 1 / ((g w_m^i)^n - 1), period 8
-  Fr t2 = fp_mul(fp_mul(a.alpha2, fp_sub(z, Fr::one())), l1inv[i]);
-  out[i] = fp_add(acc, t2);
+  // acc / Z_H(x) + alpha^2 (z - 1) / (n (x - 1)); zh_inv: device table 1 / ((g w_m^i)^n - 1), period 8
+  out[i] = fp_mul_add(acc, a.zh_inv[i & 7], fp_mul(a.alpha2, fp_sub(z, Fr::one())), l1inv[i]);
 }
 
 void quotient_evals(capgpu_ctx* ctx, const Fr* coset, const Fr* sel, const Fr* sig, const Fr* xs, const Fr* l1inv, size_t m,
