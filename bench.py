@@ -300,7 +300,9 @@ def side_measurements(args, torch, ctxs, pk, srs, circ, wires_dev, wires, pubs, 
         "fmul_microbench_gmul_per_s": calib["gfmul_per_s"],
         "frac_of_fmul_microbench": (madds_per_launch * MADD_F_MULS / sec_per_launch * 1e-9 / calib["gfmul_per_s"]) if sec_per_launch > 0 else None,
         "note": "peak = IMAD issue rate with operands in the reuse cache; a Montgomery product with register operands "
-                "sustains fmul_microbench (all warp slots busy), which is the practical ceiling of this kernel",
+                "sustains fmul_microbench (all warp slots busy), which is the practical ceiling of this kernel; 'achieved' "
+                "counts the ALGORITHMIC work of SURVEY 8(d) (10 products x 136 wide MADs per addition) - the kernel itself "
+                "executes 1304 per addition (two dedicated squarings, one fused a*b - c*d with a single reduction)",
         "algorithmic": f"{MADD_F_MULS} field products x {F_MUL_WIDE_MADS} wide MADs per bucket addition, {madds_per_launch:.0f} additions per launch",
         "avg_launch_ms": acc["ms_per_proof"] / launches,
     }
