@@ -59,3 +59,16 @@ def test_srs_powers_and_limbs():
     assert B.from_limbs(B.to_limbs(x)) == x
     assert B.from_mont(B.to_mont(12345, B.R), B.R) == 12345
     assert B.from_mont(B.to_mont(12345, B.Q), B.Q) == 12345
+
+
+def test_g1_known_answers_from_the_alt_bn128_precompile_vectors():
+    """External pin of the curve arithmetic: 2G and 3G on alt_bn128 (= ark-bn254's G1, generator
+    (1, 2)) as published with the EIP-196 ecAdd / ecMul precompile test vectors."""
+    g2 = (0x030644E72E131A029B85045B68181585D97816A916871CA8D3C208C16D87CFD3,
+          0x15ED738C0E0A7C92E7845F96B2AE9C0A68A6A449E3538FC7FF3EBF7A5A18A2C4)
+    g3 = (0x0769BF9AC56BEA3FF40232BCB1B6BD159315D84715B8E679F2D355961915ABF0,
+          0x2AB799BEE0489429554FDB7C8D086475319E63B40B9C5B57CDF1FF3DD9FE2261)
+    assert B.g1_add(B.G1_GEN, B.G1_GEN) == g2
+    assert B.g1_mul(B.G1_GEN, 2) == g2
+    assert B.g1_add(g2, B.G1_GEN) == g3 and B.g1_mul(B.G1_GEN, 3) == g3
+    assert B.g1_is_on_curve(g2) and B.g1_is_on_curve(g3)
