@@ -31,7 +31,6 @@ import subprocess
 import sys
 import threading
 import time
-from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -53,8 +52,9 @@ def parse_args():
     ap.add_argument("--impl", default="capgpu", choices=["capgpu", "reference"])
     ap.add_argument("--workload", default="transfer_2x2")
     ap.add_argument("--batch", type=int, default=64, help="independent notes per GPU per step")
-    ap.add_argument("--ctxs", type=int, default=16, help="prover contexts (host thread + CUDA stream) per GPU")
-    ap.add_argument("--cpu-sample", type=int, default=2, help="proofs in the cpu_baseline sample (0 disables)")
+    ap.add_argument("--ctxs", type=int, default=4, help="prover contexts (host thread + CUDA stream) per GPU")
+    ap.add_argument("--group", type=int, default=8, help="notes a context proves in lockstep (capgpu_ctx_set_group)")
+    ap.add_argument("--cpu-sample", type=int, default=-1, help="proofs in the cpu_baseline sample (-1: one per host thread, 0 disables)")
     ap.add_argument("--witness", default="dense", choices=["dense", "sparse"],
                     help="dense: uniform witness (the headline workload); sparse: 45%% of gate inputs unused (zero variable), "
                          "half of the fresh inputs boolean — closer to jf-relation gadget circuits; exercises the evaluation-form commitments")
@@ -142,6 +142,8 @@ def run_capgpu(args):
     circ, circs, wires, pubs, bl = build_workload(args.workload, args.witness)
     n = circ.n
     ctxs = [device.Context(local) for _ in range(args.ctxs)]
+    for c in ctxs:
+        c.set_group(args.group)
     ctx0 = ctxs[0]
     lib = ctx0.lib
     srs = plonk.PlonkKzgSnark.universal_setup(ctx0, n + 2, TAU)
@@ -149,10 +151,11 @@ def run_capgpu(args):
     if args.no_lagrange:
         pk.set_lagrange(False)
 
-    # inputs: pinned host copies (e2e) and device-resident copies (value)
-    wires_pin = [torch.from_numpy(w.view(np.int64)).pin_memory() for w in wires]
-    wires_dev = [t.cuda(non_blocking=True) for t in wires_pin]
+    # value: witness columns resident in HBM.  e2e: every note of a step has its OWN pageable host
+    # buffer (what a Rust caller's Vec<Fr> is); they are re-used from step to step.
+    wires_dev = [torch.from_numpy(w.view(np.int64)).cuda() for w in wires]
     torch.cuda.synchronize()
+    wires_host = [wires[i % N_WITNESSES].copy() for i in range(args.batch)]
     ext = b"bench-ext-msg"
     ext_buf = (ctypes.c_uint8 * len(ext)).from_buffer_copy(ext)
     from ctypes import byref, c_void_p
@@ -163,39 +166,38 @@ def run_capgpu(args):
         if on_device:
             rc = lib.capgpu_prove_dev(c.h, pk.h, c_void_p(wires_dev[w].data_ptr()), device._ptr(pubs[w]), device._ptr(bl[w]), ext_buf, len(ext), byref(out))
         else:
-            rc = lib.capgpu_prove(c.h, pk.h, c_void_p(wires_pin[w].data_ptr()), device._ptr(pubs[w]), device._ptr(bl[w]), ext_buf, len(ext), byref(out))
+            rc = lib.capgpu_prove(c.h, pk.h, device._ptr(wires_host[i % args.batch]), device._ptr(pubs[w]), device._ptr(bl[w]), ext_buf, len(ext), byref(out))
         _lib.check(rc, c.h)
 
-    pool = ThreadPoolExecutor(max_workers=args.ctxs)
-    proofs = [_lib.Proof() for _ in range(args.ctxs)]
-
-    def worker(ci: int, on_device: bool):
-        for i in range(ci, args.batch, args.ctxs):
-            prove_one(ci, i, on_device, proofs[ci])
-
-    batch_wptrs = [wires_pin[i % N_WITNESSES].data_ptr() for i in range(args.batch)]
+    batch_dptrs = [wires_dev[i % N_WITNESSES].data_ptr() for i in range(args.batch)]
     batch_pubs = [pubs[i % N_WITNESSES] for i in range(args.batch)]
     batch_bl = [bl[i % N_WITNESSES] for i in range(args.batch)]
     batch_msgs = [ext] * args.batch
+    queue = plonk.ProvingQueue(ctxs, pk)
 
-    def step(on_device: bool):
-        if not on_device:
-            # end to end through the call a host application makes: ONE capgpu_prove_batch over the
-            # step's notes (host pointers in, proofs out; worker threads live inside the library)
-            plonk.prove_batch_raw(ctxs, pk, batch_wptrs, batch_pubs, batch_bl, batch_msgs)
-            return
-        futs = [pool.submit(worker, ci, on_device) for ci in range(args.ctxs)]
-        for f in futs:
-            f.result()
+    def steps_dev(k: int):
+        # one capgpu_prove_batch_dev per step: the contexts' worker threads live inside the library
+        for _ in range(k):
+            plonk.prove_batch_raw(ctxs, pk, batch_dptrs, batch_pubs, batch_bl, batch_msgs, on_device=True)
+
+    def steps_e2e(k: int):
+        # end to end through the asynchronous API a host application uses: capgpu_submit copies each
+        # note's pageable wire buffer into the pinned ring (H2D from there), capgpu_wait returns the
+        # proof (D2H of commitments / evaluations); consecutive steps are pipelined by the queue
+        tickets = []
+        for _ in range(k):
+            for i in range(args.batch):
+                tickets.append(queue.submit(wires_host[i], batch_pubs[i], batch_bl[i], ext))
+        for t in tickets:
+            queue.wait(t)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(on_device: bool, sample_clocks: bool):
-        for _ in range(args.warmup):
-            step(on_device)
+    def timed(run, sample_clocks: bool):
+        run(args.warmup)
         # one sampler per job (rank 0's GPU): eight nvidia-smi pollers contend on the driver and
         # visibly slow multi-GPU runs
         sampler = ClockSampler(local) if (sample_clocks and rank == 0) else None
@@ -205,29 +207,36 @@ def run_capgpu(args):
             sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(args.steps):
-            step(on_device)
+        t0 = time.perf_counter()
+        run(args.steps)
         e1.record()
         barrier()
-        ms = e0.elapsed_time(e1)
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        ms = max(e0.elapsed_time(e1), 0.0)
         clocks = sampler.stop() if sampler else None
         launches = sum(c.launch_count for c in ctxs) - launches0
         ms, launches = shard.reduce_timing(ms, launches, device="cuda")  # max / sum over ranks
-        return ms, clocks, launches
+        return ms, clocks, launches, wall_ms
 
-    # sanity: the proof from the device-resident path equals the host-buffer path
+    # sanity: lockstep, device-resident and host-buffer proofs are the same bytes
     pa, pb = _lib.Proof(), _lib.Proof()
     prove_one(0, 1, True, pa)
     prove_one(0, 1, False, pb)
     assert bytes(pa) == bytes(pb), "device-resident and host-buffer proofs differ"
+    k = args.group + 1
+    grp, st = plonk.prove_batch_raw(ctxs, pk, batch_dptrs[:k], batch_pubs[:k], batch_bl[:k], batch_msgs[:k], on_device=True)
+    assert bytes(grp[1]) == bytes(pa) and not any(st), "lockstep group proof differs from the single proof"
 
-    ms_dev, clocks, launches = timed(True, True)
-    ms_e2e, _, _ = timed(False, False)
+    ms_dev, clocks, launches, _ = timed(steps_dev, True)
+    qs0 = queue.stats()
+    ms_e2e, _, _, wall_e2e = timed(steps_e2e, False)
+    qs1 = queue.stats()
     total = world * args.batch * args.steps
     value = total / (ms_dev * 1e-3)
     e2e_value = total / (ms_e2e * 1e-3)
     h2d = args.batch * (5 * n * 32 + pubs[0].nbytes + 17 * 32 + len(ext))
     d2h = args.batch * (13 * 64 + 10 * 32 + 4)
+    notes_q = max(qs1["submitted"] - qs0["submitted"], 1)
 
     line = {
         "metric": METRIC, "value": value, "unit": "proofs/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -235,18 +244,27 @@ def run_capgpu(args):
         "dtype": "u32 (254-bit Montgomery, 8 x 32-bit limbs)", "data": "synthetic",
         "config": {
             "workload": f"{args.workload}: TurboPlonk prove, domain n=2^{circ.log_n}, 5 wires, 13 selectors, {circ.num_inputs} public inputs, BN254",
-            "notes_per_gpu_per_step": args.batch, "prover_ctxs_per_gpu": args.ctxs, "distinct_witnesses": N_WITNESSES,
+            "notes_per_gpu_per_step": args.batch, "prover_ctxs_per_gpu": args.ctxs, "lockstep_group": args.group,
+            "host_threads_per_gpu": args.ctxs, "distinct_witnesses": N_WITNESSES,
             "witness": args.witness, "wire_commitments": "coefficient form" if args.no_lagrange else "evaluation form (Lagrange commit key)",
             "parallelism": f"{world} x independent-note shards, no collective",
-            "cache": "per-proof working set (126 MB workspace + 159 MB cached pk cosets) exceeds the 126 MB L2; no flush needed",
+            "cache": "per-group working set (>1 GB workspace + 159 MB cached pk cosets) exceeds the 126 MB L2; no flush needed",
         },
         "clocks": clocks,
-        "e2e": {"value": e2e_value, "unit": "proofs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+        "e2e": {"value": e2e_value, "unit": "proofs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
+                "api": "capgpu_submit / capgpu_wait (asynchronous queue), one distinct PAGEABLE host buffer per note",
+                "host_copy_ms_per_note": (qs1["copy_ms"] - qs0["copy_ms"]) / notes_q,
+                "host_wait_for_ring_slot_ms_per_note": (qs1["wait_slot_ms"] - qs0["wait_slot_ms"]) / notes_q,
+                "avg_lockstep_group": notes_q / max(qs1["groups"] - qs0["groups"], 1), "wall_ms_per_step": wall_e2e / args.steps},
         "gpu_launches": launches,
     }
+    queue.close()
 
     if rank == 0 and not args.no_extras:
-        line.update(side_measurements(args, torch, ctxs, pk, srs, circ, wires_dev, wires, pubs, bl, prove_one, world))
+        def prove_group0():
+            g = args.group
+            plonk.prove_batch_raw(ctxs[:1], pk, batch_dptrs[:g], batch_pubs[:g], batch_bl[:g], batch_msgs[:g], on_device=True)
+        line.update(side_measurements(args, torch, ctxs, pk, srs, circ, wires_dev, wires, pubs, bl, prove_one, world, prove_group0))
     if rank == 0:
         emit(json.dumps(line))
     if world > 1:
@@ -254,7 +272,7 @@ def run_capgpu(args):
         dist.destroy_process_group()
 
 
-def side_measurements(args, torch, ctxs, pk, srs, circ, wires_dev, wires, pubs, bl, prove_one, world):
+def side_measurements(args, torch, ctxs, pk, srs, circ, wires_dev, wires, pubs, bl, prove_one, world, prove_group0):
     """Roofline of the dominant kernel, NTT bandwidth, 2^17 MSM latency, CPU baseline."""
     from ctypes import byref, c_double, c_uint64, c_void_p
     from cap_b200 import _lib, device, field
@@ -270,12 +288,13 @@ def side_measurements(args, torch, ctxs, pk, srs, circ, wires_dev, wires, pubs, 
     calib = ctx.calibrate()
     imad_peak = max(calib["gimad_per_s"], calib["gimad_wide_per_s"])  # G lane-ops / s, measured here
 
-    # ---- per-kernel times of one proof, kernels alone on the GPU (profiling serialises the ctx)
+    # ---- per-kernel times of one lockstep group (the unit the timed steps are made of), kernels alone
+    # on the GPU (profiling serialises the ctx); reported per proof
+    prove_group0()
     _lib.check(lib.capgpu_profile_enable(ctx.h, 1), ctx.h)
-    reps = 3
-    p = _lib.Proof()
-    for i in range(reps):
-        prove_one(0, i, True, p)
+    reps = 2 * args.group
+    for _ in range(2):
+        prove_group0()
     prof = {}
     for pid, name in enumerate(["msm_accumulate", "ntt", "quotient", "msm_sort", "msm_reduce", "grand_product"]):
         ms, cnt, units = c_double(), c_uint64(), c_double()
@@ -365,33 +384,58 @@ def side_measurements(args, torch, ctxs, pk, srs, circ, wires_dev, wires, pubs, 
     out["single_proof_latency_ms"] = statistics.median(lat[1:])
 
     # ---- CPU baseline: the C restatement of the reference's CPU algorithms on this host's cores
-    if world == 1 and args.cpu_sample > 0:
+    if world == 1 and args.cpu_sample != 0:
         out["cpu_baseline"] = cpu_baseline(args, circ, pk, srs, wires, pubs, bl, args.cpu_sample)
     return out
 
 
+def cpu_prove_concurrently(circ, sel, sig, sig_e, k, srs_xy, sc, gc, wires, pubs, bl, count: int, cores: int):
+    """Proves `count` notes on `cores` host threads the way the reference does
+    (/root/reference/src/utils/params_builder.rs:195-233: a rayon parallel iterator over the notes,
+    every note proved independently): a pool of workers, one note each.  With at least `cores` notes
+    in flight every proof runs single-threaded (no synchronisation loss -- measured 1.45x the
+    throughput of one note at a time on all threads); fewer notes split the threads among them.
+    Returns elapsed seconds."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import cpu  # checker / baseline leg only
+    conc = min(count, cores)
+    per = max(1, cores // conc)
+
+    def one(i):
+        w = i % N_WITNESSES
+        rc, _ = cpu.prove(circ.log_n, circ.num_inputs, sel, sig, sig_e, k, srs_xy, sc, gc, wires[w], pubs[w], bl[w], b"bench-ext-msg", nthreads=per)
+        assert rc == 0
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(conc) as ex:
+        list(ex.map(one, range(count)))
+    return time.perf_counter() - t0, conc, per
+
+
 def cpu_baseline(args, circ, pk, srs, wires, pubs, bl, sample: int):
     from cap_b200 import field, plonk
-    from oracle import cpu  # checker / baseline leg only
     threads = os.cpu_count() or 1
     sel, sig, sc, gc = pk.export()
     srs_xy = srs.export()
     sig_e = np.stack([field.fr_to_mont_array(s) for s in plonk.sigma_evals(circ)])
     k = field.fr_to_mont_array(circ.k)
-    t0 = time.perf_counter()
-    for i in range(sample):
-        w = i % N_WITNESSES
-        rc, _ = cpu.prove(circ.log_n, circ.num_inputs, sel, sig, sig_e, k, srs_xy, sc, gc, wires[w], pubs[w], bl[w], b"bench-ext-msg", nthreads=threads)
-        assert rc == 0
-    dt = time.perf_counter() - t0
-    return {"value": sample / dt, "unit": "proofs/s", "cores": threads, "kind": "port",
-            "sample": f"{sample} proofs of the same workload, {dt:.1f} s, oracle/c/plonk_cpu.c (arkworks / jf-plonk algorithms restated in C, pthreads)"}
+    count = sample if sample > 0 else threads
+    dt, conc, per = cpu_prove_concurrently(circ, sel, sig, sig_e, k, srs_xy, sc, gc, wires, pubs, bl, count, threads)
+    return {"value": count / dt, "unit": "proofs/s", "cores": threads, "kind": "port",
+            "sample": f"{count} proofs of the same workload, {conc} at a time x {per} thread(s) each, {dt:.1f} s, oracle/c/plonk_cpu.c "
+                      f"(arkworks / jf-plonk algorithms restated in C, pthreads)"}
 
 
 # --------------------------------------------------------------------------------------------
 # reference arm: the reference's CPU path (C restatement; no Rust toolchain / crates here)
 # --------------------------------------------------------------------------------------------
 def run_reference(args):
+    """Times the reference's own CPU implementation of the path on this box's host cores, notes
+    proved concurrently as the reference does (params_builder.rs:195-233).  One step = a bounded
+    sample of the step's workload: max(1, cores / 4) notes; all steps are fed to the worker pool
+    back to back (as a rayon iterator over K x sample notes would be), so every core stays busy
+    across step boundaries.  Under torchrun only rank 0 runs (and prints) -- the CPU arm has one
+    host to use whatever N is, so its value does not depend on N."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -405,26 +449,22 @@ def run_reference(args):
     sig_e = np.stack([field.fr_to_mont_array(s) for s in plonk.sigma_evals(circ)])
     sel, sig, sc, gc = cpu.preprocess(circ.log_n, sel_e, sig_e, srs_xy, nthreads=threads)
     k = field.fr_to_mont_array(circ.k)
-
-    def step(i):
-        w = i % N_WITNESSES
-        rc, _ = cpu.prove(circ.log_n, circ.num_inputs, sel, sig, sig_e, k, srs_xy, sc, gc, wires[w], pubs[w], bl[w], b"bench-ext-msg", nthreads=threads)
-        assert rc == 0
-
-    for i in range(args.warmup):
-        step(i)
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        step(i)
-    dt = time.perf_counter() - t0
-    value = args.steps / dt
-    sample = f"1 proof per step ({args.steps} timed), all {threads} host threads, oracle/c/plonk_cpu.c"
+    per_step = max(1, threads // 4)
+    if args.warmup > 0:
+        cpu_prove_concurrently(circ, sel, sig, sig_e, k, srs_xy, sc, gc, wires, pubs, bl, min(threads, max(1, args.warmup) * per_step), threads)
+    count = args.steps * per_step
+    dt, conc, per = cpu_prove_concurrently(circ, sel, sig, sig_e, k, srs_xy, sc, gc, wires, pubs, bl, count, threads)
+    value = count / dt
+    sample = (f"{per_step} notes per step x {args.steps} steps = {count} proofs, {conc} in flight x {per} thread(s) each on {threads} host threads, "
+              f"{dt:.1f} s, oracle/c/plonk_cpu.c")
     emit(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "proofs/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u64 (254-bit Montgomery, 4 x 64-bit limbs)", "data": "synthetic",
         "config": {"workload": f"{args.workload}: TurboPlonk prove, domain n=2^{circ.log_n}, 5 wires, 13 selectors, {circ.num_inputs} public inputs, BN254",
-                   "note": "reference CPU algorithms (arkworks 0.3 / jf-plonk 0.1.2) restated in C: the Rust crates are not vendored and no Rust toolchain exists in this image"},
+                   "notes_per_step": per_step,
+                   "note": "reference CPU algorithms (arkworks 0.3 / jf-plonk 0.1.2) restated in C: the Rust crates are not vendored and no Rust toolchain exists in this image; "
+                           "notes proved concurrently across the host threads like the reference's rayon loop; one host whatever --gpus is"},
         "cpu_baseline": {"value": value, "unit": "proofs/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))

@@ -20,6 +20,7 @@ EXPORTS = [
     "capgpu_prove", "capgpu_job_begin", "capgpu_job_round1", "capgpu_job_round2", "capgpu_job_round3",
     "capgpu_job_round4", "capgpu_job_round5", "capgpu_job_end", "capgpu_debug_read", "capgpu_launch_count",
     "capgpu_calibrate", "capgpu_prove_dev", "capgpu_profile_enable", "capgpu_profile_read", "capgpu_ctx_set_latency_mode", "capgpu_g1_sum_dev", "capgpu_srs_upload_compressed", "capgpu_prove_batch",
+    "capgpu_ctx_set_group", "capgpu_pk_info", "capgpu_prove_batch_dev", "capgpu_queue_create", "capgpu_queue_destroy", "capgpu_submit", "capgpu_poll", "capgpu_wait", "capgpu_queue_stats",
 ]
 
 
@@ -47,11 +48,13 @@ _lib = None
 
 
 def load() -> ctypes.CDLL:
-    """Loads libcapgpu.so, building it first if the sources are newer / it is absent."""
+    """Loads libcapgpu.so.  `build.build()` runs first: it is a no-op when the stamp beside the
+    library equals the digest of the current sources and flags, and rebuilds otherwise, so a stale
+    library is never loaded silently (CAPGPU_NO_BUILD=1 skips the check, e.g. on a box without nvcc)."""
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    if not os.environ.get("CAPGPU_NO_BUILD") or not os.path.exists(LIB_PATH):
         from . import build as _build
         _build.build()
     if not os.path.exists(LIB_PATH):
@@ -89,6 +92,15 @@ def load() -> ctypes.CDLL:
         "capgpu_profile_enable": (c_int, [c_void_p, c_int]),
         "capgpu_profile_read": (c_int, [c_void_p, c_int, POINTER(c_double), POINTER(c_uint64), POINTER(c_double)]),
         "capgpu_prove_batch": (c_int, [c_void_p, c_size_t, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+        "capgpu_prove_batch_dev": (c_int, [c_void_p, c_size_t, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+        "capgpu_ctx_set_group": (c_int, [c_void_p, c_int]),
+        "capgpu_pk_info": (c_int, [c_void_p, POINTER(c_uint), POINTER(c_size_t), c_void_p]),
+        "capgpu_queue_create": (c_int, [c_void_p, c_size_t, c_void_p, c_size_t, POINTER(c_void_p)]),
+        "capgpu_queue_destroy": (None, [c_void_p]),
+        "capgpu_submit": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, POINTER(c_uint64)]),
+        "capgpu_poll": (c_int, [c_void_p, c_uint64, POINTER(c_int)]),
+        "capgpu_wait": (c_int, [c_void_p, c_uint64, POINTER(Proof)]),
+        "capgpu_queue_stats": (c_int, [c_void_p, POINTER(c_uint64), POINTER(c_uint64), POINTER(c_uint64), POINTER(c_double), POINTER(c_double)]),
         "capgpu_job_begin": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_void_p)]),
         "capgpu_job_round1": (c_int, [c_void_p, c_void_p, c_void_p]),
         "capgpu_job_round2": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

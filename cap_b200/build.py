@@ -14,8 +14,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libcapgpu.so")
-SOURCES = ["capi.cu", "ntt.cu", "msm.cu", "poly.cu", "prover.cu"]
-HEADERS = ["fp.cuh", "ec.cuh", "common.cuh", "keccak.h", "transcript.h", "poly.cuh", os.path.join("..", "..", "include", "capgpu.h")]
+SOURCES = ["capi.cu", "ntt.cu", "msm.cu", "poly.cu", "prover.cu", "formats.cu"]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))) + [os.path.join("..", "..", "include", "capgpu.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-O2", "--threads", "0",
@@ -63,7 +63,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
     if failed:
         raise RuntimeError("nvcc failed building libcapgpu.so")
-    subprocess.run([nvcc, "-shared", "-o", OUT, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"], check=True)
+    subprocess.run([nvcc, "-shared", "-o", OUT, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-ldl"], check=True)
     with open(stamp, "w") as f:
         f.write(dig)
     return OUT

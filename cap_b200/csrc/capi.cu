@@ -1,6 +1,7 @@
 // extern "C" surface of libcapgpu: context management, standalone NTT entry point,
 // calibration kernels.  (MSM entry points live in msm.cu, prover entry points in prover.cu.)
 #include "common.cuh"
+#include <stdlib.h>
 
 using namespace capgpu;
 
@@ -33,6 +34,7 @@ extern "C" int capgpu_ctx_create(int device, capgpu_ctx** out) {
     cudaDeviceProp prop;
     CAPGPU_CUDA(cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
+    if (const char* e = getenv("CAPGPU_GROUP")) { int g = atoi(e); if (g >= 1 && g <= 64) ctx->group = g; }
     ctx->pinned_bytes = 1 << 16;
     CAPGPU_CUDA(cudaMallocHost(&ctx->pinned, ctx->pinned_bytes));
     CAPGPU_CUDA(cudaEventCreateWithFlags(&ctx->sync_ev, cudaEventBlockingSync | cudaEventDisableTiming));
@@ -51,6 +53,7 @@ extern "C" void capgpu_ctx_destroy(capgpu_ctx* ctx) {
   ctx->ntt_tmp.release(); ctx->ntt_io.release();
   ctx->msm_scalars.release(); ctx->msm_digits.release(); ctx->msm_counts.release();
   ctx->msm_entries.release(); ctx->msm_buckets.release(); ctx->msm_partials.release(); ctx->msm_out.release();
+  ctx->msm_flat.release();
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->sync_ev) cudaEventDestroy(ctx->sync_ev);
   if (ctx->pe0) cudaEventDestroy(ctx->pe0);

@@ -67,6 +67,7 @@ struct capgpu_ctx {
   // optional per-kernel timing (capgpu_profile_enable): CUDA events on the ctx stream around
   // the instrumented launches, accumulated per kernel class
   bool latency_mode = false;  // prover MSMs favour depth over total work (capgpu_ctx_set_latency_mode)
+  int group = 8;              // notes proved in lockstep by capgpu_prove_batch / the queue (capgpu_ctx_set_group)
   bool profile = false;
   cudaEvent_t pe0 = nullptr, pe1 = nullptr;
   double prof_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};

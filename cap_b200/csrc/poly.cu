@@ -11,10 +11,11 @@ namespace capgpu {
 // Prover::mask_polynomial: p(X) + (b0 + b1 X + ..)(X^n - 1); also clears the padding tail.
 // polys: rows of `stride` elements holding n coefficients; row r gets blinders[boff[r] ..].
 // ------------------------------------------------------------------------------------------
-__global__ void blind_kernel(Fr* polys, size_t stride, size_t n, int nrows, int nb, BlindArgs args) {
-  int r = blockIdx.x;
+__global__ void blind_kernel(Fr* polys, size_t stride, size_t n, int nrows, int G, int nb, const BlindArgs* __restrict__ argv) {
+  const int r = blockIdx.x, g = blockIdx.y;
   if (r >= nrows) return;
-  Fr* p = polys + (size_t)r * stride;
+  const BlindArgs& args = argv[g];
+  Fr* p = polys + ((size_t)r * G + g) * stride;
   for (size_t t = threadIdx.x; t < stride - n; t += blockDim.x) {
     Fr v = Fr::zero();
     if ((int)t < nb && r < args.rows_blinded) {
@@ -35,9 +36,15 @@ __global__ void blind_kernel(Fr* polys, size_t stride, size_t n, int nrows, int 
 // inverse prefix denominators backward (gp_finish).  15 products per row, 1 inversion total.
 // ------------------------------------------------------------------------------------------
 __global__ void gp_terms(const Fr* __restrict__ wires, size_t wstride, const Fr* __restrict__ sig_eval, const Fr* __restrict__ omega_pows,
-                         size_t n, GpArgs a, Fr* num, Fr* den) {
+                         size_t n, int G, const GpArgs* __restrict__ argv, Fr* num, Fr* den) {
   size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
+  const int g = blockIdx.y;
+  const GpArgs& a = argv[g];
+  wires += (size_t)g * wstride;
+  wstride *= G;  // row (i, g) of the [5][G] block
+  num += (size_t)g * n;
+  den += (size_t)g * n;
   Fr bw = fp_mul(a.beta, omega_pows[j]);
   Fr nu, de;
 #pragma unroll
@@ -53,10 +60,12 @@ __global__ void gp_terms(const Fr* __restrict__ wires, size_t wstride, const Fr*
   den[j] = de;
 }
 
-__global__ void gp_chunk_prod(const Fr* __restrict__ num, const Fr* __restrict__ den, size_t n, size_t L, Fr* cn, Fr* cd) {
+__global__ void gp_chunk_prod(const Fr* __restrict__ num, const Fr* __restrict__ den, size_t n, size_t L, Fr* cn, Fr* cd, size_t cstride) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t T = n / L;
   if (t >= T) return;
+  num += (size_t)blockIdx.y * n; den += (size_t)blockIdx.y * n;
+  cn += (size_t)blockIdx.y * cstride; cd += (size_t)blockIdx.y * cstride;
   Fr pn = num[t * L], pd = den[t * L];
   for (size_t j = t * L + 1; j < (t + 1) * L; j++) {
     pn = fp_mul(pn, num[j]);
@@ -69,8 +78,9 @@ __global__ void gp_chunk_prod(const Fr* __restrict__ num, const Fr* __restrict__
 // One block of 1024 threads over T chunk products (each thread owns `per` consecutive chunks).
 // Out: cn[t] = prod_{u<t} cn_in[u] (numerator prefix at the chunk start),
 //      cd[t] = 1 / prod_{u<=t} cd_in[u] (inverse denominator prefix at the chunk end).
-__global__ void __launch_bounds__(1024) gp_scan(Fr* cn, Fr* cd, int T) {
+__global__ void __launch_bounds__(1024) gp_scan(Fr* cn, Fr* cd, int T, size_t cstride) {
   extern __shared__ uint32_t gp_sm[];
+  cn += (size_t)blockIdx.x * cstride; cd += (size_t)blockIdx.x * cstride;
   Fr* sn = reinterpret_cast<Fr*>(gp_sm);  // 1024 entries
   Fr* sd = sn + 1024;                     // 1024 entries
   __shared__ Fr inv_total;
@@ -112,10 +122,12 @@ __global__ void __launch_bounds__(1024) gp_scan(Fr* cn, Fr* cd, int T) {
 }
 
 __global__ void gp_finish(const Fr* __restrict__ num, const Fr* __restrict__ den, size_t n, size_t L, const Fr* __restrict__ cn,
-                          const Fr* __restrict__ cd, Fr* z) {
+                          const Fr* __restrict__ cd, size_t cstride, Fr* z) {
   size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   size_t T = n / L;
   if (t >= T) return;
+  num += (size_t)blockIdx.y * n; den += (size_t)blockIdx.y * n; z += (size_t)blockIdx.y * n;
+  cn += (size_t)blockIdx.y * cstride; cd += (size_t)blockIdx.y * cstride;
   Fr pn = cn[t];
   for (size_t j = t * L; j < (t + 1) * L; j++) {
     z[j] = pn;  // N_j = prod_{i<j} num_i
@@ -128,20 +140,20 @@ __global__ void gp_finish(const Fr* __restrict__ num, const Fr* __restrict__ den
   }
 }
 
-void grand_product(capgpu_ctx* ctx, const Fr* wires, size_t wstride, const Fr* sig_eval, const Fr* omega_pows, size_t n,
-                   const GpArgs& a, Fr* num, Fr* den, Fr* cn, Fr* cd, Fr* z) {
-  // chunks of 8 rows (fewer for tiny domains): T = n / L chunk products, scanned by one CTA
+void grand_product(capgpu_ctx* ctx, const Fr* wires, size_t wstride, const Fr* sig_eval, const Fr* omega_pows, size_t n, int G,
+                   const GpArgs* args, Fr* num, Fr* den, Fr* cn, Fr* cd, size_t cstride, Fr* z) {
+  // chunks of 8 rows (fewer for tiny domains): T = n / L chunk products, scanned by one CTA per proof
   size_t L = n >= 16 ? 8 : 1;
   size_t T = n / L;
-  ProfScope prof(ctx, PROF_GRAND_PRODUCT, (double)n);
-  gp_terms<<<ceil_div(n, 128), 128, 0, ctx->stream>>>(wires, wstride, sig_eval, omega_pows, n, a, num, den);
+  ProfScope prof(ctx, PROF_GRAND_PRODUCT, (double)n * G);
+  gp_terms<<<dim3(ceil_div(n, 128), G), 128, 0, ctx->stream>>>(wires, wstride, sig_eval, omega_pows, n, G, args, num, den);
   CAPGPU_LAUNCH_CHECK(ctx);
-  gp_chunk_prod<<<ceil_div(T, 128), 128, 0, ctx->stream>>>(num, den, n, L, cn, cd);
+  gp_chunk_prod<<<dim3(ceil_div(T, 128), G), 128, 0, ctx->stream>>>(num, den, n, L, cn, cd, cstride);
   CAPGPU_LAUNCH_CHECK(ctx);
   CAPGPU_CUDA(cudaFuncSetAttribute(gp_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * 1024 * (int)sizeof(Fr)));
-  gp_scan<<<1, 1024, 2 * 1024 * sizeof(Fr), ctx->stream>>>(cn, cd, (int)T);
+  gp_scan<<<G, 1024, 2 * 1024 * sizeof(Fr), ctx->stream>>>(cn, cd, (int)T, cstride);
   CAPGPU_LAUNCH_CHECK(ctx);
-  gp_finish<<<ceil_div(T, 128), 128, 0, ctx->stream>>>(num, den, n, L, cn, cd, z);
+  gp_finish<<<dim3(ceil_div(T, 128), G), 128, 0, ctx->stream>>>(num, den, n, L, cn, cd, cstride, z);
   CAPGPU_LAUNCH_CHECK(ctx);
 }
 
@@ -160,15 +172,21 @@ __device__ __forceinline__ Fr pow5(const Fr& w) {
 
 __global__ void __launch_bounds__(128) quotient_kernel(const Fr* __restrict__ coset /*7 x m: w0..w4, pi, z*/, const Fr* __restrict__ sel /*13 x m*/,
                                                        const Fr* __restrict__ sig /*5 x m*/, const Fr* __restrict__ xs /*m*/,
-                                                       const Fr* __restrict__ l1inv /*m*/, size_t m, QuotArgs a, Fr* out) {
+                                                       const Fr* __restrict__ l1inv /*m*/, const Fr* __restrict__ zh_inv /*8*/, size_t m,
+                                                       int G, const QuotArgs* __restrict__ argv, Fr* out) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= m) return;
+  const int g = blockIdx.y;
+  const QuotArgs& a = argv[g];
+  coset += (size_t)g * m;          // row (j, g) of the [7][G] block is coset[j * cm + ..]
+  const size_t cm = (size_t)G * m;
+  out += (size_t)g * m;
   Fr w[5];
 #pragma unroll
-  for (int j = 0; j < 5; j++) w[j] = coset[(size_t)j * m + i];
+  for (int j = 0; j < 5; j++) w[j] = coset[(size_t)j * cm + i];
   // gate part
   // the twelve selector products are summed two at a time with one Montgomery reduction per pair
-  Fr acc = fp_add(sel[11 * m + i], coset[5 * m + i]);  // q_c + PI
+  Fr acc = fp_add(sel[11 * m + i], coset[5 * cm + i]);  // q_c + PI
   acc = fp_add(acc, fp_mul_add(sel[0 * m + i], w[0], sel[1 * m + i], w[1]));
   acc = fp_add(acc, fp_mul_add(sel[2 * m + i], w[2], sel[3 * m + i], w[3]));
   Fr w01 = fp_mul(w[0], w[1]);
@@ -178,10 +196,10 @@ __global__ void __launch_bounds__(128) quotient_kernel(const Fr* __restrict__ co
   acc = fp_add(acc, fp_mul_add(sel[8 * m + i], pow5(w[2]), sel[9 * m + i], pow5(w[3])));
   acc = fp_add(acc, fp_mul_sub(sel[12 * m + i], fp_mul(fp_mul(w01, w23), w[4]), sel[10 * m + i], w[4]));
   // permutation part
-  Fr z = coset[6 * m + i];
+  Fr z = coset[6 * cm + i];
   size_t inext = i + 8;
   if (inext >= m) inext -= m;
-  Fr zn = coset[6 * m + inext];
+  Fr zn = coset[6 * cm + inext];
   Fr bx = fp_mul(a.beta, xs[i]);
   Fr r1 = z, r2 = zn;
 #pragma unroll
@@ -193,13 +211,13 @@ __global__ void __launch_bounds__(128) quotient_kernel(const Fr* __restrict__ co
   }
   acc = fp_add(acc, fp_mul(a.alpha, fp_sub(r1, r2)));
   // acc / Z_H(x) + alpha^2 (z - 1) / (n (x - 1)); zh_inv: device table 1 / ((g w_m^i)^n - 1), period 8
-  out[i] = fp_mul_add(acc, a.zh_inv[i & 7], fp_mul(a.alpha2, fp_sub(z, Fr::one())), l1inv[i]);
+  out[i] = fp_mul_add(acc, zh_inv[i & 7], fp_mul(a.alpha2, fp_sub(z, Fr::one())), l1inv[i]);
 }
 
-void quotient_evals(capgpu_ctx* ctx, const Fr* coset, const Fr* sel, const Fr* sig, const Fr* xs, const Fr* l1inv, size_t m,
-                    const QuotArgs& a, Fr* out) {
-  ProfScope prof(ctx, PROF_QUOTIENT, (double)m);
-  quotient_kernel<<<ceil_div(m, 128), 128, 0, ctx->stream>>>(coset, sel, sig, xs, l1inv, m, a, out);
+void quotient_evals(capgpu_ctx* ctx, const Fr* coset, const Fr* sel, const Fr* sig, const Fr* xs, const Fr* l1inv, const Fr* zh_inv,
+                    size_t m, int G, const QuotArgs* args, Fr* out) {
+  ProfScope prof(ctx, PROF_QUOTIENT, (double)m * G);
+  quotient_kernel<<<dim3(ceil_div(m, 128), G), 128, 0, ctx->stream>>>(coset, sel, sig, xs, l1inv, zh_inv, m, G, args, out);
   CAPGPU_LAUNCH_CHECK(ctx);
 }
 
@@ -223,9 +241,16 @@ void coset_tables(capgpu_ctx* ctx, const Fr* omega_m, size_t m, const Fr& gen, c
 //   t_i(X) + b_i X^(n+2) - b_{i-1}
 // flag[0] |= 1 if any coefficient above 5n+7 is non-zero, |= 2 if coefficient 5n+7 is zero.
 // ------------------------------------------------------------------------------------------
-__global__ void split_kernel(const Fr* __restrict__ t, size_t n, size_t m, Fr* split, size_t stride, BlindArgs args, uint32_t* flag) {
+__global__ void split_kernel(const Fr* __restrict__ t, size_t n, size_t m, int G, Fr* split, size_t stride,
+                             const BlindArgs* __restrict__ argv, uint32_t* flag) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t deg = 5 * n + 7;
+  const int g = blockIdx.y;
+  const BlindArgs& args = argv[g];
+  t += (size_t)g * m;
+  flag += g;
+  split += (size_t)g * stride;  // row (r, g) at split[r * rs + ..]
+  const size_t rs = (size_t)G * stride;
   if (i < m) {
     Fr c = t[i];
     if (i > deg && !c.is_zero()) atomicOr(flag, 1u);
@@ -235,24 +260,24 @@ __global__ void split_kernel(const Fr* __restrict__ t, size_t n, size_t m, Fr* s
       size_t o = i - r * (n + 2);
       if (r > 4) { r = 4; o = i - 4 * (n + 2); }
       if (o == 0 && r > 0) c = fp_sub(c, args.b[r - 1]);
-      split[r * stride + o] = c;
+      split[r * rs + o] = c;
     }
   }
   // tails: row r < 4 gets b_r at position n+2, zeros after; row 4 is zero from n on
   if (i < 5 * (stride - n)) {
     size_t r = i / (stride - n), o = n + i % (stride - n);
     if (r < 4) {
-      if (o == n + 2) split[r * stride + o] = args.b[r];
-      else if (o > n + 2) split[r * stride + o] = Fr::zero();
+      if (o == n + 2) split[r * rs + o] = args.b[r];
+      else if (o > n + 2) split[r * rs + o] = Fr::zero();
     } else {
-      split[r * stride + o] = Fr::zero();
+      split[r * rs + o] = Fr::zero();
     }
   }
 }
 
-void split_quotient(capgpu_ctx* ctx, const Fr* t, size_t n, size_t m, Fr* split, size_t stride, const BlindArgs& args, uint32_t* flag) {
-  CAPGPU_CUDA(cudaMemsetAsync(flag, 0, sizeof(uint32_t), ctx->stream));
-  split_kernel<<<ceil_div(m, 256), 256, 0, ctx->stream>>>(t, n, m, split, stride, args, flag);
+void split_quotient(capgpu_ctx* ctx, const Fr* t, size_t n, size_t m, int G, Fr* split, size_t stride, const BlindArgs* args, uint32_t* flag) {
+  CAPGPU_CUDA(cudaMemsetAsync(flag, 0, G * sizeof(uint32_t), ctx->stream));
+  split_kernel<<<dim3(ceil_div(m, 256), G), 256, 0, ctx->stream>>>(t, n, m, G, split, stride, args, flag);
   CAPGPU_LAUNCH_CHECK(ctx);
 }
 
@@ -263,9 +288,11 @@ void split_quotient(capgpu_ctx* ctx, const Fr* t, size_t n, size_t m, Fr* split,
 // ------------------------------------------------------------------------------------------
 constexpr int EVAL_SPLIT = 16;
 
-__global__ void __launch_bounds__(128) eval_kernel(EvalArgs a, Fr* partials) {
+__global__ void __launch_bounds__(128) eval_kernel(const EvalArgs* __restrict__ argv, Fr* partials) {
   __shared__ Fr sm[128];
   const int b = blockIdx.y;
+  const EvalArgs& a = argv[blockIdx.z];
+  partials += (size_t)blockIdx.z * 160;
   const Fr* p = a.poly[b];
   const size_t len = a.len[b];
   const Fr x = a.x[b];
@@ -291,17 +318,19 @@ __global__ void __launch_bounds__(128) eval_kernel(EvalArgs a, Fr* partials) {
 }
 
 __global__ void eval_sum_kernel(const Fr* __restrict__ partials, int count, Fr* out) {
-  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  int b = threadIdx.x;
   if (b >= count) return;
+  partials += (size_t)blockIdx.x * 160;
+  out += (size_t)blockIdx.x * 16;
   Fr acc = partials[b * EVAL_SPLIT];
   for (int i = 1; i < EVAL_SPLIT; i++) acc = fp_add(acc, partials[b * EVAL_SPLIT + i]);
   out[b] = acc;
 }
 
-void evaluate(capgpu_ctx* ctx, const EvalArgs& a, int count, Fr* out, Fr* scratch) {
-  eval_kernel<<<dim3(EVAL_SPLIT, count), 128, 0, ctx->stream>>>(a, scratch);
+void evaluate(capgpu_ctx* ctx, const EvalArgs* args, int count, int G, Fr* out, Fr* scratch) {
+  eval_kernel<<<dim3(EVAL_SPLIT, count, G), 128, 0, ctx->stream>>>(args, scratch);
   CAPGPU_LAUNCH_CHECK(ctx);
-  eval_sum_kernel<<<1, 32, 0, ctx->stream>>>(scratch, count, out);
+  eval_sum_kernel<<<G, 32, 0, ctx->stream>>>(scratch, count, out);
   CAPGPU_LAUNCH_CHECK(ctx);
 }
 
@@ -311,30 +340,35 @@ void evaluate(capgpu_ctx* ctx, const EvalArgs& a, int count, Fr* out, Fr* scratc
 //   lin   = sum_s a_s q_s + cz z + cs sigma_4 + sum_i ct_i t_i
 //   batch = lin + sum_{i<5} v^(i+1) w_i + sum_{i<4} v^(6+i) sigma_i
 // ------------------------------------------------------------------------------------------
-__global__ void lin_batch_kernel(LinArgs a, Fr* lin, Fr* batch) {
+__global__ void lin_batch_kernel(const LinArgs* __restrict__ argv, const Fr* __restrict__ sel, const Fr* __restrict__ sig, size_t n,
+                                 size_t len, Fr* lin, Fr* batch, size_t ostride) {
   size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= a.len) return;
-  Fr acc = fp_mul(a.polys[6 * a.pstride + j], a.cz);  // z poly (row 6), n+3 coefficients
-  if (j < a.n) {
+  if (j >= len) return;
+  const LinArgs& a = argv[blockIdx.y];
+  lin += (size_t)blockIdx.y * ostride;
+  batch += (size_t)blockIdx.y * ostride;
+  Fr acc = fp_mul(a.polys[6 * a.rstride + j], a.cz);  // z poly (row 6), n+3 coefficients
+  if (j < n) {
 #pragma unroll
-    for (int s = 0; s < 13; s++) acc = fp_add(acc, fp_mul(a.sel[(size_t)s * a.n + j], a.cs_sel[s]));
-    acc = fp_add(acc, fp_mul(a.sig[4 * a.n + j], a.csig));
+    for (int s = 0; s < 13; s++) acc = fp_add(acc, fp_mul(sel[(size_t)s * n + j], a.cs_sel[s]));
+    acc = fp_add(acc, fp_mul(sig[4 * n + j], a.csig));
   }
 #pragma unroll
-  for (int i = 0; i < 5; i++) acc = fp_add(acc, fp_mul(a.split[(size_t)i * a.pstride + j], a.ct[i]));
+  for (int i = 0; i < 5; i++) acc = fp_add(acc, fp_mul(a.split[(size_t)i * a.rstride + j], a.ct[i]));
   lin[j] = acc;
   Fr bt = acc;
 #pragma unroll
-  for (int i = 0; i < 5; i++) bt = fp_add(bt, fp_mul(a.polys[(size_t)i * a.pstride + j], a.vp[i]));
-  if (j < a.n) {
+  for (int i = 0; i < 5; i++) bt = fp_add(bt, fp_mul(a.polys[(size_t)i * a.rstride + j], a.vp[i]));
+  if (j < n) {
 #pragma unroll
-    for (int i = 0; i < 4; i++) bt = fp_add(bt, fp_mul(a.sig[(size_t)i * a.n + j], a.vp[5 + i]));
+    for (int i = 0; i < 4; i++) bt = fp_add(bt, fp_mul(sig[(size_t)i * n + j], a.vp[5 + i]));
   }
   batch[j] = bt;
 }
 
-void lin_batch(capgpu_ctx* ctx, const LinArgs& a, Fr* lin, Fr* batch) {
-  lin_batch_kernel<<<ceil_div(a.len, 128), 128, 0, ctx->stream>>>(a, lin, batch);
+void lin_batch(capgpu_ctx* ctx, const LinArgs* args, const Fr* sel, const Fr* sig, size_t n, size_t len, int G, Fr* lin, Fr* batch,
+               size_t ostride) {
+  lin_batch_kernel<<<dim3(ceil_div(len, 128), G), 128, 0, ctx->stream>>>(args, sel, sig, n, len, lin, batch, ostride);
   CAPGPU_LAUNCH_CHECK(ctx);
 }
 
@@ -346,8 +380,10 @@ void lin_batch(capgpu_ctx* ctx, const LinArgs& a, Fr* lin, Fr* batch) {
 // ------------------------------------------------------------------------------------------
 constexpr int DIV_CHUNK = 16;
 
-__global__ void __launch_bounds__(128) div_chunk_sums(DivArgs a, Fr* totals, size_t tmax) {
-  const int b = blockIdx.y;
+__global__ void __launch_bounds__(128) div_chunk_sums(const DivArgs* __restrict__ argv, int count, Fr* totals, size_t tmax) {
+  const DivArgs& a = argv[blockIdx.y / count];
+  const int b = blockIdx.y % count;
+  totals += (size_t)(blockIdx.y - b) * tmax;
   const size_t len = a.len[b];
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t T = (len + DIV_CHUNK - 1) / DIV_CHUNK;
@@ -365,9 +401,11 @@ __global__ void __launch_bounds__(128) div_chunk_sums(DivArgs a, Fr* totals, siz
 }
 
 // totals[t] <- sum_{u > t} totals[u]   (one CTA per polynomial)
-__global__ void __launch_bounds__(1024) div_scan(DivArgs a, Fr* totals, size_t tmax) {
+__global__ void __launch_bounds__(1024) div_scan(const DivArgs* __restrict__ argv, int count, Fr* totals, size_t tmax) {
   __shared__ Fr sm[1024];
-  const int b = blockIdx.x;
+  const DivArgs& a = argv[blockIdx.x / count];
+  const int b = blockIdx.x % count;
+  totals += (size_t)(blockIdx.x - b) * tmax;
   const size_t T = (a.len[b] + DIV_CHUNK - 1) / DIV_CHUNK;
   Fr* v = totals + b * tmax;
   const size_t per = (T + blockDim.x - 1) / blockDim.x;
@@ -391,8 +429,10 @@ __global__ void __launch_bounds__(1024) div_scan(DivArgs a, Fr* totals, size_t t
   }
 }
 
-__global__ void __launch_bounds__(128) div_finish(DivArgs a, const Fr* __restrict__ carries, size_t tmax) {
-  const int b = blockIdx.y;
+__global__ void __launch_bounds__(128) div_finish(const DivArgs* __restrict__ argv, int count, const Fr* __restrict__ carries, size_t tmax) {
+  const DivArgs& a = argv[blockIdx.y / count];
+  const int b = blockIdx.y % count;
+  carries += (size_t)(blockIdx.y - b) * tmax;
   const size_t len = a.len[b];
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const size_t T = (len + DIV_CHUNK - 1) / DIV_CHUNK;
@@ -412,50 +452,49 @@ __global__ void __launch_bounds__(128) div_finish(DivArgs a, const Fr* __restric
   }
 }
 
-void divide_linear(capgpu_ctx* ctx, const DivArgs& a, int count, Fr* scratch, size_t tmax) {
-  size_t maxlen = 0;
-  for (int i = 0; i < count; i++) maxlen = a.len[i] > maxlen ? a.len[i] : maxlen;
+void divide_linear(capgpu_ctx* ctx, const DivArgs* args, int count, int G, size_t maxlen, Fr* scratch, size_t tmax) {
   const size_t T = (maxlen + DIV_CHUNK - 1) / DIV_CHUNK;
   CAPGPU_REQUIRE(T <= tmax, "division scratch too small");
-  dim3 grid(ceil_div(T, 128), count);
-  div_chunk_sums<<<grid, 128, 0, ctx->stream>>>(a, scratch, tmax);
+  dim3 grid(ceil_div(T, 128), count * G);
+  div_chunk_sums<<<grid, 128, 0, ctx->stream>>>(args, count, scratch, tmax);
   CAPGPU_LAUNCH_CHECK(ctx);
-  div_scan<<<count, 1024, 0, ctx->stream>>>(a, scratch, tmax);
+  div_scan<<<count * G, 1024, 0, ctx->stream>>>(args, count, scratch, tmax);
   CAPGPU_LAUNCH_CHECK(ctx);
-  div_finish<<<grid, 128, 0, ctx->stream>>>(a, scratch, tmax);
+  div_finish<<<grid, 128, 0, ctx->stream>>>(args, count, scratch, tmax);
   CAPGPU_LAUNCH_CHECK(ctx);
 }
 
 // public-input evaluations: zeros except rows < num_inputs
-__global__ void fill_pi_kernel(Fr* dst, size_t n, const Fr* __restrict__ pub, size_t l) {
+__global__ void fill_pi_kernel(Fr* dst, size_t stride, size_t n, const Fr* __restrict__ pub, size_t pub_stride, size_t l) {
   size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
-  dst[j] = j < l ? pub[j] : Fr::zero();
+  dst[(size_t)blockIdx.y * stride + j] = j < l ? pub[(size_t)blockIdx.y * pub_stride + j] : Fr::zero();
 }
 
-void fill_pi(capgpu_ctx* ctx, Fr* dst, size_t n, const Fr* pub, size_t l) {
-  fill_pi_kernel<<<ceil_div(n, 256), 256, 0, ctx->stream>>>(dst, n, pub, l);
+void fill_pi(capgpu_ctx* ctx, Fr* dst, size_t stride, size_t n, int G, const Fr* pub, size_t pub_stride, size_t l) {
+  fill_pi_kernel<<<dim3(ceil_div(n, 256), G), 256, 0, ctx->stream>>>(dst, stride, n, pub, pub_stride, l);
   CAPGPU_LAUNCH_CHECK(ctx);
 }
 
 // Evaluation-form commitment of a masked wire polynomial: scalars of the bases P_0, P_1, P_n, P_{n+1}
 // appended after the n evaluations of each row: (b0 + b1 X)(X^n - 1) = -b0 - b1 X + b0 X^n + b1 X^(n+1).
-__global__ void lagrange_tail_kernel(Fr* evals, size_t stride, size_t n, BlindArgs args) {
+__global__ void lagrange_tail_kernel(Fr* evals, size_t stride, size_t n, int G, const BlindArgs* __restrict__ argv) {
   int r = threadIdx.x >> 1, t = threadIdx.x & 1;
+  const BlindArgs& args = argv[blockIdx.x];
   if (r >= args.rows_blinded) return;
   Fr b = args.b[r * 2 + t];
-  Fr* row = evals + (size_t)r * stride + n;
+  Fr* row = evals + ((size_t)r * G + blockIdx.x) * stride + n;
   row[t] = fp_neg(b);
   row[2 + t] = b;
 }
 
-void lagrange_tail(capgpu_ctx* ctx, Fr* evals, size_t stride, size_t n, const BlindArgs& args) {
-  lagrange_tail_kernel<<<1, 32, 0, ctx->stream>>>(evals, stride, n, args);
+void lagrange_tail(capgpu_ctx* ctx, Fr* evals, size_t stride, size_t n, int G, const BlindArgs* args) {
+  lagrange_tail_kernel<<<G, 32, 0, ctx->stream>>>(evals, stride, n, G, args);
   CAPGPU_LAUNCH_CHECK(ctx);
 }
 
-void blind(capgpu_ctx* ctx, Fr* polys, size_t stride, size_t n, int nrows, int nb, const BlindArgs& args) {
-  blind_kernel<<<nrows, 32, 0, ctx->stream>>>(polys, stride, n, nrows, nb, args);
+void blind(capgpu_ctx* ctx, Fr* polys, size_t stride, size_t n, int nrows, int G, int nb, const BlindArgs* args) {
+  blind_kernel<<<dim3(nrows, G), 32, 0, ctx->stream>>>(polys, stride, n, nrows, G, nb, args);
   CAPGPU_LAUNCH_CHECK(ctx);
 }
 

@@ -1,4 +1,10 @@
 // Argument blocks and launchers of the polynomial-side prover kernels (poly.cu).
+//
+// Every launcher works on a GROUP of G proofs proved in lockstep over one proving key: vectors
+// of the same kind are stored row-major as [row kind][proof][elements] (row (r, g) at
+// (r * G + g) * stride), so the NTT / MSM launches of a round see one uniform batch of rows, and
+// the per-proof scalars (Fiat-Shamir challenges, blinders, evaluation points) live in device
+// arrays indexed by the proof's slot g = blockIdx.y.
 #pragma once
 #include "common.cuh"
 
@@ -17,7 +23,6 @@ struct GpArgs {
 struct QuotArgs {
   Fr alpha, alpha2, beta, gamma;
   Fr k[5];
-  const Fr* zh_inv;  // 8 entries (device)
 };
 
 struct EvalArgs {
@@ -27,11 +32,9 @@ struct EvalArgs {
 };
 
 struct LinArgs {
-  const Fr* polys;  // 7 rows (w0..w4, pi, z), stride pstride
-  const Fr* split;  // 5 rows, stride pstride
-  const Fr* sel;    // 13 x n coefficients
-  const Fr* sig;    // 5 x n coefficients
-  size_t pstride, n, len;
+  const Fr* polys;  // row (r, g) of the [7][G] polynomial block for this proof's g: polys + r * rstride
+  const Fr* split;  // row (i, g) of the [5][G] split block: split + i * rstride
+  size_t rstride;   // G * row stride
   Fr cs_sel[13];
   Fr cz, csig;
   Fr ct[5];
@@ -46,17 +49,26 @@ struct DivArgs {
   Fr xinv[2];
 };
 
-void blind(capgpu_ctx* ctx, Fr* polys, size_t stride, size_t n, int nrows, int nb, const BlindArgs& args);
-void lagrange_tail(capgpu_ctx* ctx, Fr* evals, size_t stride, size_t n, const BlindArgs& args);
-void fill_pi(capgpu_ctx* ctx, Fr* dst, size_t n, const Fr* pub, size_t l);
-void grand_product(capgpu_ctx* ctx, const Fr* wires, size_t wstride, const Fr* sig_eval, const Fr* omega_pows, size_t n,
-                   const GpArgs& a, Fr* num, Fr* den, Fr* cn, Fr* cd, Fr* z);
-void quotient_evals(capgpu_ctx* ctx, const Fr* coset, const Fr* sel, const Fr* sig, const Fr* xs, const Fr* l1inv, size_t m,
-                    const QuotArgs& a, Fr* out);
+// polys: [nrows][G] rows of `stride` elements; args[g]
+void blind(capgpu_ctx* ctx, Fr* polys, size_t stride, size_t n, int nrows, int G, int nb, const BlindArgs* args);
+void lagrange_tail(capgpu_ctx* ctx, Fr* evals, size_t stride, size_t n, int G, const BlindArgs* args);
+// dst: G rows (stride `stride`) of n evaluations; pub: G rows of pub_stride elements
+void fill_pi(capgpu_ctx* ctx, Fr* dst, size_t stride, size_t n, int G, const Fr* pub, size_t pub_stride, size_t l);
+// wires: [5][G] rows of wstride; num / den / z: G rows of n; cn / cd: G rows of cstride
+void grand_product(capgpu_ctx* ctx, const Fr* wires, size_t wstride, const Fr* sig_eval, const Fr* omega_pows, size_t n, int G,
+                   const GpArgs* args, Fr* num, Fr* den, Fr* cn, Fr* cd, size_t cstride, Fr* z);
+// coset: [7][G] rows of m; out: G rows of m
+void quotient_evals(capgpu_ctx* ctx, const Fr* coset, const Fr* sel, const Fr* sig, const Fr* xs, const Fr* l1inv, const Fr* zh_inv,
+                    size_t m, int G, const QuotArgs* args, Fr* out);
 void coset_tables(capgpu_ctx* ctx, const Fr* omega_m, size_t m, const Fr& gen, const Fr& n_mont, Fr* xs, Fr* l1inv);
-void split_quotient(capgpu_ctx* ctx, const Fr* t, size_t n, size_t m, Fr* split, size_t stride, const BlindArgs& args, uint32_t* flag);
-void evaluate(capgpu_ctx* ctx, const EvalArgs& a, int count, Fr* out, Fr* scratch /* 16 * count */);
-void lin_batch(capgpu_ctx* ctx, const LinArgs& a, Fr* lin, Fr* batch);
-void divide_linear(capgpu_ctx* ctx, const DivArgs& a, int count, Fr* scratch /* count * tmax */, size_t tmax);
+// t: G rows of m; split: [5][G] rows of stride; flag[g]
+void split_quotient(capgpu_ctx* ctx, const Fr* t, size_t n, size_t m, int G, Fr* split, size_t stride, const BlindArgs* args, uint32_t* flag);
+// out: G rows of 16 (10 used); scratch: G x 160
+void evaluate(capgpu_ctx* ctx, const EvalArgs* args, int count, int G, Fr* out, Fr* scratch);
+// sel / sig: the key's coefficient polynomials (13 x n, 5 x n); lin / batch: G rows of ostride
+void lin_batch(capgpu_ctx* ctx, const LinArgs* args, const Fr* sel, const Fr* sig, size_t n, size_t len, int G, Fr* lin, Fr* batch,
+               size_t ostride);
+// scratch: G x count x tmax
+void divide_linear(capgpu_ctx* ctx, const DivArgs* args, int count, int G, size_t maxlen, Fr* scratch, size_t tmax);
 
 }  // namespace capgpu

@@ -4,13 +4,31 @@
 // freeze.rs:151).  Every vector-sized step is a kernel (ntt.cu, msm.cu, poly.cu); the host
 // only hashes the transcript and derives O(1) scalars between rounds, and reads back 64-byte
 // commitments / 32-byte evaluations.  [UPSTREAM-RECALL: round structure per SURVEY.md App. A.]
+//
+// LOCKSTEP GROUPS.  A context proves G independent notes over one proving key at the same time:
+// every round is issued ONCE for the group, with all vectors of one kind stored as
+// [row kind][proof][elements] so that the round's NTT and MSM launches are single batches of
+// 5G / 6G / 7G rows, and the per-proof scalars (challenges, blinders, evaluation points) sit in
+// device arrays indexed by the proof's slot.  The commitments of the permutation product, the
+// openings and the quotient transform -- batches of 1 or 2 vectors when one proof is proved alone
+// -- then fill the GPU like the wire commitments do, and one host thread drives G proofs with the
+// five host round trips of one.  G = 1 is the single-proof path (capgpu_prove, the round API).
+// The reference's counterpart is the rayon loop over notes of
+// /root/reference/src/utils/params_builder.rs:195-233.
 #include <string.h>
 
 #include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <deque>
+#include <memory>
+#include <mutex>
 #include <thread>
+#include <unordered_map>
 #include <vector>
 
 #include "poly.cuh"
+#include "prover.h"
 #include "transcript.h"
 
 using namespace capgpu;
@@ -25,18 +43,9 @@ static inline HFr host_omega(unsigned log_n) {
   return w;
 }
 
-struct capgpu_pk {
-  int device = 0;
-  unsigned log_n = 0;
-  size_t n = 0, m = 0, num_inputs = 0;
-  const capgpu_srs* srs = nullptr;
-  capgpu_srs* lag = nullptr;  // Lagrange-basis commit key [L_0..L_{n-1}, P_0, P_1, P_n, P_{n+1}] (owned)
-  bool use_lag = true;
-  Fr *sel_coef = nullptr, *sig_coef = nullptr, *sig_eval = nullptr, *sel_coset = nullptr, *sig_coset = nullptr;
-  Fr *xs = nullptr, *l1inv = nullptr, *zh_inv = nullptr, *omega_n = nullptr;
-  HFr k[5];
-  uint64_t sel_comms[13][8], sig_comms[5][8];
-  std::vector<uint8_t> vk_bytes;
+struct ProofState {
+  HFr beta, gamma, alpha, zeta, v;
+  HFr evals[10];
 };
 
 struct capgpu_job {
@@ -44,232 +53,335 @@ struct capgpu_job {
   const capgpu_pk* pk = nullptr;
   int round = 0;
   bool busy = false;
-  size_t n = 0, m = 0, NP = 0, num_inputs = 0;
+  int cap = 0;  // proofs the workspace can hold
+  int G = 0;    // proofs of the group being proved (row (r, g) of a [rows][G] block sits at (r * G + g) * stride)
+  size_t n = 0, m = 0, NP = 0, num_inputs = 0, pub_stride = 0, cstride = 0;
   DevBuf buf;  // one allocation, carved below
   Fr *wires_eval = nullptr, *polys = nullptr, *z_eval = nullptr, *coset = nullptr, *t = nullptr, *split = nullptr;
-  Fr *lin = nullptr, *batch = nullptr, *open = nullptr, *shifted = nullptr;
+  Fr *lin = nullptr, *batch = nullptr, *open = nullptr;  // open: [2][G] rows (opening, shifted opening)
   Fr *num = nullptr, *den = nullptr, *cn = nullptr, *cd = nullptr, *ntt_tmp = nullptr, *evals_dev = nullptr, *pub_dev = nullptr;
   Fr *eval_scratch = nullptr, *div_scratch = nullptr;
   size_t div_tmax = 0;
   G1Affine* comms_dev = nullptr;
   uint32_t* flag = nullptr;
-  HFr beta, gamma, alpha, zeta, v;
-  HFr evals[10];
+  // per-proof kernel arguments: device arrays and their pinned host mirrors
+  BlindArgs *d_blind = nullptr, *h_blind = nullptr;
+  GpArgs *d_gp = nullptr, *h_gp = nullptr;
+  QuotArgs *d_quot = nullptr, *h_quot = nullptr;
+  EvalArgs *d_eval = nullptr, *h_eval = nullptr;
+  LinArgs *d_lin = nullptr, *h_lin = nullptr;
+  DivArgs *d_div = nullptr, *h_div = nullptr;
+  void* pinned = nullptr;  // host mirrors + read-back area
+  G1Affine* h_comms = nullptr;
+  Fr* h_evals = nullptr;
+  Fr* h_pub = nullptr;
+  uint32_t* h_flag = nullptr;
+  std::vector<ProofState> st;
 };
 
 void capgpu_job_free_internal(capgpu_job* job) {
   if (!job) return;
   job->buf.release();
+  if (job->pinned) cudaFreeHost(job->pinned);
   delete job;
 }
 
 namespace {
 
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-capgpu_job* job_acquire(capgpu_ctx* ctx, const capgpu_pk* pk) {
+capgpu_job* job_acquire(capgpu_ctx* ctx, const capgpu_pk* pk, int G) {
   CAPGPU_REQUIRE(pk->device == ctx->device, "proving key lives on another device");
+  CAPGPU_REQUIRE(G >= 1 && G <= CAPGPU_MAX_GROUP, "group size out of range");
   capgpu_job* job = ctx->cached_job;
   if (job && job->busy) throw CodeError{CAPGPU_ERR_STATE};
-  if (job && (job->n != pk->n || job->num_inputs < pk->num_inputs)) {
+  if (job && (job->n != pk->n || job->num_inputs < pk->num_inputs || job->cap < G)) {
     capgpu_job_free_internal(job);
     ctx->cached_job = job = nullptr;
   }
   if (!job) {
-    job = new capgpu_job();
+    std::unique_ptr<capgpu_job, void (*)(capgpu_job*)> holder(new capgpu_job(), capgpu_job_free_internal);
+    job = holder.get();
     job->ctx = ctx;
+    job->cap = G;
     job->n = pk->n;
     job->m = pk->m;
     job->NP = pk->n + 8;
     job->num_inputs = pk->num_inputs;
-    const size_t n = job->n, m = job->m, NP = job->NP;
+    job->pub_stride = align_up(pk->num_inputs + 1, 8);
+    const size_t n = job->n, m = job->m, NP = job->NP, C = (size_t)G;
+    job->cstride = n / 8 + 8;
     job->div_tmax = (NP + 15) / 16 + 1;
-    size_t elems = 6 * NP + 7 * NP + n + 7 * m + m + 5 * NP + 4 * NP + 2 * n + 2 * (n / 8 + 8) + 7 * m + 16 + 160 + 2 * job->div_tmax +
-                   align_up(pk->num_inputs + 1, 8);
-    size_t bytes = elems * sizeof(Fr) + 8 * sizeof(G1Affine) + 256;
+    const size_t elems = C * (6 * NP + 7 * NP + n + 7 * m + m + 5 * NP + 4 * NP + 2 * n + 2 * job->cstride + 7 * m + 16 + 160 +
+                              2 * job->div_tmax + job->pub_stride);
+    const size_t arg_bytes = C * (align_up(sizeof(BlindArgs), 32) + align_up(sizeof(GpArgs), 32) + align_up(sizeof(QuotArgs), 32) +
+                                  align_up(sizeof(EvalArgs), 32) + align_up(sizeof(LinArgs), 32) + align_up(sizeof(DivArgs), 32));
+    const size_t bytes = elems * sizeof(Fr) + arg_bytes + 5 * C * sizeof(G1Affine) + align_up(C * sizeof(uint32_t), 32) + 256;
     job->buf.reserve(bytes);
     Fr* p = job->buf.as<Fr>();
     auto take = [&](size_t cnt) { Fr* r = p; p += cnt; return r; };
-    job->wires_eval = take(6 * NP);  // rows of n evaluations, stride NP (tail: blinding scalars of the Lagrange commit)
-    job->polys = take(7 * NP);
-    job->z_eval = take(n);
-    job->coset = take(7 * m);
-    job->t = take(m);
-    job->split = take(5 * NP);
-    job->lin = take(NP); job->batch = take(NP); job->open = take(NP); job->shifted = take(NP);
-    job->num = take(n); job->den = take(n);
-    job->cn = take(n / 8 + 8); job->cd = take(n / 8 + 8);
-    job->ntt_tmp = take(7 * m);
-    job->evals_dev = take(16);
-    job->eval_scratch = take(160);
-    job->div_scratch = take(2 * job->div_tmax);
-    job->pub_dev = take(align_up(pk->num_inputs + 1, 8));
-    job->comms_dev = reinterpret_cast<G1Affine*>(p);
-    job->flag = reinterpret_cast<uint32_t*>(job->comms_dev + 8);
-    ctx->cached_job = job;
+    job->wires_eval = take(C * 6 * NP);  // [6][G] rows of n evaluations (tail: blinding scalars of the Lagrange commit)
+    job->polys = take(C * 7 * NP);       // [7][G]: w0..w4, PI, z
+    job->z_eval = take(C * n);
+    job->coset = take(C * 7 * m);
+    job->t = take(C * m);
+    job->split = take(C * 5 * NP);
+    job->lin = take(C * NP); job->batch = take(C * NP); job->open = take(C * 2 * NP);
+    job->num = take(C * n); job->den = take(C * n);
+    job->cn = take(C * job->cstride); job->cd = take(C * job->cstride);
+    job->ntt_tmp = take(C * 7 * m);
+    job->evals_dev = take(C * 16);
+    job->eval_scratch = take(C * 160);
+    job->div_scratch = take(C * 2 * job->div_tmax);
+    job->pub_dev = take(C * job->pub_stride);
+    char* q = reinterpret_cast<char*>(p);
+    auto take_bytes = [&](size_t b) { char* r = q; q += align_up(b, 32); return r; };
+    job->d_blind = reinterpret_cast<BlindArgs*>(take_bytes(C * sizeof(BlindArgs)));
+    job->d_gp = reinterpret_cast<GpArgs*>(take_bytes(C * sizeof(GpArgs)));
+    job->d_quot = reinterpret_cast<QuotArgs*>(take_bytes(C * sizeof(QuotArgs)));
+    job->d_eval = reinterpret_cast<EvalArgs*>(take_bytes(C * sizeof(EvalArgs)));
+    job->d_lin = reinterpret_cast<LinArgs*>(take_bytes(C * sizeof(LinArgs)));
+    job->d_div = reinterpret_cast<DivArgs*>(take_bytes(C * sizeof(DivArgs)));
+    job->comms_dev = reinterpret_cast<G1Affine*>(take_bytes(5 * C * sizeof(G1Affine)));
+    job->flag = reinterpret_cast<uint32_t*>(take_bytes(C * sizeof(uint32_t)));
+    // pinned mirrors
+    const size_t pin_bytes = arg_bytes + 5 * C * sizeof(G1Affine) + C * 16 * sizeof(Fr) + C * job->pub_stride * sizeof(Fr) +
+                             align_up(C * sizeof(uint32_t), 32) + 256;
+    CAPGPU_CUDA(cudaMallocHost(&job->pinned, pin_bytes));
+    q = static_cast<char*>(job->pinned);
+    job->h_blind = reinterpret_cast<BlindArgs*>(take_bytes(C * sizeof(BlindArgs)));
+    job->h_gp = reinterpret_cast<GpArgs*>(take_bytes(C * sizeof(GpArgs)));
+    job->h_quot = reinterpret_cast<QuotArgs*>(take_bytes(C * sizeof(QuotArgs)));
+    job->h_eval = reinterpret_cast<EvalArgs*>(take_bytes(C * sizeof(EvalArgs)));
+    job->h_lin = reinterpret_cast<LinArgs*>(take_bytes(C * sizeof(LinArgs)));
+    job->h_div = reinterpret_cast<DivArgs*>(take_bytes(C * sizeof(DivArgs)));
+    job->h_comms = reinterpret_cast<G1Affine*>(take_bytes(5 * C * sizeof(G1Affine)));
+    job->h_evals = reinterpret_cast<Fr*>(take_bytes(C * 16 * sizeof(Fr)));
+    job->h_pub = reinterpret_cast<Fr*>(take_bytes(C * job->pub_stride * sizeof(Fr)));
+    job->h_flag = reinterpret_cast<uint32_t*>(take_bytes(C * sizeof(uint32_t)));
+    job->st.resize(C);
+    ctx->cached_job = holder.release();
   }
   job->pk = pk;
   job->round = 0;
+  job->G = G;
   job->busy = true;
   return job;
 }
 
-void job_begin(capgpu_job* job, const uint64_t* wires, const uint64_t* pub_inputs, bool wires_on_device = false) {
-  capgpu_ctx* ctx = job->ctx;
-  const capgpu_pk* pk = job->pk;
-  const size_t n = job->n;
-  CAPGPU_CUDA(cudaMemcpy2DAsync(job->wires_eval, job->NP * sizeof(Fr), wires, n * sizeof(Fr), n * sizeof(Fr), 5,
-                                wires_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream));
-  if (pk->num_inputs)
-    CAPGPU_CUDA(cudaMemcpyAsync(job->pub_dev, pub_inputs, pk->num_inputs * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
-  fill_pi(ctx, job->wires_eval + 5 * job->NP, n, job->pub_dev, pk->num_inputs);
-  job->round = 1;
+template <class T>
+void upload_args(capgpu_job* job, T* dev, const T* host) {
+  CAPGPU_CUDA(cudaMemcpyAsync(dev, host, job->G * sizeof(T), cudaMemcpyHostToDevice, job->ctx->stream));
 }
 
-void read_points(capgpu_job* job, int count, uint64_t* out_xy) {
-  capgpu_ctx* ctx = job->ctx;
-  CAPGPU_CUDA(cudaMemcpyAsync(ctx->pinned, job->comms_dev, count * sizeof(G1Affine), cudaMemcpyDeviceToHost, ctx->stream));
-  ctx_wait(ctx);
-  memcpy(out_xy, ctx->pinned, count * sizeof(G1Affine));
-}
-
-void round1(capgpu_job* job, const uint64_t* blinders10, uint64_t* wire_comms) {
-  if (job->round != 1) throw CodeError{CAPGPU_ERR_STATE};
+// notes[g]: wire values (5 x n, host or device) and public inputs of proof g
+void job_begin(capgpu_job* job, const NoteIn* notes) {
   capgpu_ctx* ctx = job->ctx;
   const capgpu_pk* pk = job->pk;
   const size_t n = job->n, NP = job->NP;
-  // 5 wire polynomials + the public-input polynomial: one batched INTT
-  ntt_device(ctx, pk->log_n, job->wires_eval, n, NP, job->polys, NP, job->ntt_tmp, 6, true, false);
-  BlindArgs ba;
-  memcpy(ba.b, blinders10, 10 * sizeof(Fr));
-  ba.rows_blinded = 5;
-  blind(ctx, job->polys, NP, n, 6, 2, ba);
+  const int G = job->G;
+  for (int g = 0; g < G; g++) {
+    // rows (i, g), i < 5: destination pitch G * NP
+    CAPGPU_CUDA(cudaMemcpy2DAsync(job->wires_eval + (size_t)g * NP, (size_t)G * NP * sizeof(Fr), notes[g].wires, n * sizeof(Fr),
+                                  n * sizeof(Fr), 5, notes[g].wires_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                                  ctx->stream));
+    if (pk->num_inputs) memcpy(job->h_pub + (size_t)g * job->pub_stride, notes[g].pub_inputs, pk->num_inputs * sizeof(Fr));
+  }
+  if (pk->num_inputs)
+    CAPGPU_CUDA(cudaMemcpyAsync(job->pub_dev, job->h_pub, (size_t)G * job->pub_stride * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+  fill_pi(ctx, job->wires_eval + (size_t)5 * G * NP, NP, n, G, job->pub_dev, job->pub_stride, pk->num_inputs);
+  job->round = 1;
+}
+
+// commitments of `rows` row kinds: device order (r, g) -> out[g] + r * 8
+void read_points(capgpu_job* job, int rows, uint64_t* const* out) {
+  capgpu_ctx* ctx = job->ctx;
+  const int G = job->G;
+  CAPGPU_CUDA(cudaMemcpyAsync(job->h_comms, job->comms_dev, (size_t)rows * G * sizeof(G1Affine), cudaMemcpyDeviceToHost, ctx->stream));
+  ctx_wait(ctx);
+  for (int g = 0; g < G; g++)
+    for (int r = 0; r < rows; r++) memcpy(out[g] + 8 * r, &job->h_comms[r * G + g], sizeof(G1Affine));
+}
+
+void round1(capgpu_job* job, const uint64_t* const* blinders10, uint64_t* const* wire_comms) {
+  if (job->round != 1) throw CodeError{CAPGPU_ERR_STATE};
+  NvtxRange nv("capgpu round 1: wire polynomials + commitments");
+  capgpu_ctx* ctx = job->ctx;
+  const capgpu_pk* pk = job->pk;
+  const size_t n = job->n, NP = job->NP;
+  const int G = job->G;
+  // 5 wire polynomials + the public-input polynomial of every proof: one batched INTT
+  ntt_device(ctx, pk->log_n, job->wires_eval, n, NP, job->polys, NP, job->ntt_tmp, 6 * G, true, false);
+  for (int g = 0; g < G; g++) {
+    memcpy(job->h_blind[g].b, blinders10[g], 10 * sizeof(Fr));
+    job->h_blind[g].rows_blinded = 5;
+  }
+  upload_args(job, job->d_blind, job->h_blind);
+  blind(ctx, job->polys, NP, n, 6, G, 2, job->d_blind);
   if (pk->lag && pk->use_lag) {
     // commit from the evaluations: sum_j w_j L_j + (b0 + b1 X)(X^n - 1) at tau — the same group element as
     // the coefficient-form MSM, but zero / small witness cells cost nothing / one window
-    lagrange_tail(ctx, job->wires_eval, NP, n, ba);
-    msm_device(ctx, pk->lag, 0, job->wires_eval, n + 4, NP, 5, true, job->comms_dev, ctx->latency_mode);
+    lagrange_tail(ctx, job->wires_eval, NP, n, G, job->d_blind);
+    msm_device(ctx, pk->lag, 0, job->wires_eval, n + 4, NP, 5 * G, true, job->comms_dev, ctx->latency_mode);
   } else {
-    msm_device(ctx, pk->srs, 0, job->polys, n + 2, NP, 5, true, job->comms_dev, ctx->latency_mode);
+    msm_device(ctx, pk->srs, 0, job->polys, n + 2, NP, 5 * G, true, job->comms_dev, ctx->latency_mode);
   }
   read_points(job, 5, wire_comms);
   job->round = 2;
 }
 
-void round2(capgpu_job* job, const uint64_t* beta, const uint64_t* gamma, const uint64_t* blinders3, uint64_t* z_comm) {
+void round2(capgpu_job* job, const uint64_t* const* beta, const uint64_t* const* gamma, const uint64_t* const* blinders3,
+            uint64_t* const* z_comm) {
   if (job->round != 2) throw CodeError{CAPGPU_ERR_STATE};
+  NvtxRange nv("capgpu round 2: permutation grand product");
   capgpu_ctx* ctx = job->ctx;
   const capgpu_pk* pk = job->pk;
   const size_t n = job->n, NP = job->NP;
-  job->beta = HFr::from_limbs(beta);
-  job->gamma = HFr::from_limbs(gamma);
-  GpArgs ga;
-  ga.beta = to_dev(job->beta);
-  ga.gamma = to_dev(job->gamma);
-  for (int i = 0; i < 5; i++) ga.k[i] = to_dev(pk->k[i]);
-  grand_product(ctx, job->wires_eval, NP, pk->sig_eval, pk->omega_n, n, ga, job->num, job->den, job->cn, job->cd, job->z_eval);
-  Fr* zp = job->polys + 6 * NP;
-  ntt_device(ctx, pk->log_n, job->z_eval, n, n, zp, NP, job->ntt_tmp, 1, true, false);
-  BlindArgs ba;
-  memcpy(ba.b, blinders3, 3 * sizeof(Fr));
-  ba.rows_blinded = 1;
-  blind(ctx, zp, NP, n, 1, 3, ba);
-  msm_device(ctx, pk->srs, 0, zp, n + 3, NP, 1, true, job->comms_dev, ctx->latency_mode);
+  const int G = job->G;
+  for (int g = 0; g < G; g++) {
+    ProofState& s = job->st[g];
+    s.beta = HFr::from_limbs(beta[g]);
+    s.gamma = HFr::from_limbs(gamma[g]);
+    GpArgs& ga = job->h_gp[g];
+    ga.beta = to_dev(s.beta);
+    ga.gamma = to_dev(s.gamma);
+    for (int i = 0; i < 5; i++) ga.k[i] = to_dev(pk->k[i]);
+    memcpy(job->h_blind[g].b, blinders3[g], 3 * sizeof(Fr));
+    job->h_blind[g].rows_blinded = 1;
+  }
+  upload_args(job, job->d_gp, job->h_gp);
+  upload_args(job, job->d_blind, job->h_blind);
+  grand_product(ctx, job->wires_eval, NP, pk->sig_eval, pk->omega_n, n, G, job->d_gp, job->num, job->den, job->cn, job->cd, job->cstride,
+                job->z_eval);
+  Fr* zp = job->polys + (size_t)6 * G * NP;
+  ntt_device(ctx, pk->log_n, job->z_eval, n, n, zp, NP, job->ntt_tmp, G, true, false);
+  blind(ctx, zp, NP, n, 1, G, 3, job->d_blind);
+  msm_device(ctx, pk->srs, 0, zp, n + 3, NP, G, true, job->comms_dev, ctx->latency_mode);
   read_points(job, 1, z_comm);
   job->round = 3;
 }
 
-void round3(capgpu_job* job, const uint64_t* alpha, const uint64_t* blinders4, uint64_t* split_comms) {
+// status[g] receives CAPGPU_ERR_DEGREE for a proof whose quotient has the wrong degree (the
+// witness does not satisfy the circuit); the other proofs of the group are unaffected
+void round3(capgpu_job* job, const uint64_t* const* alpha, const uint64_t* const* blinders4, uint64_t* const* split_comms, int* status) {
   if (job->round != 3) throw CodeError{CAPGPU_ERR_STATE};
+  NvtxRange nv("capgpu round 3: quotient polynomial");
   capgpu_ctx* ctx = job->ctx;
   const capgpu_pk* pk = job->pk;
   const size_t n = job->n, m = job->m, NP = job->NP;
-  job->alpha = HFr::from_limbs(alpha);
+  const int G = job->G;
+  for (int g = 0; g < G; g++) {
+    ProofState& s = job->st[g];
+    s.alpha = HFr::from_limbs(alpha[g]);
+    QuotArgs& qa = job->h_quot[g];
+    qa.alpha = to_dev(s.alpha);
+    qa.alpha2 = to_dev(s.alpha.sqr());
+    qa.beta = to_dev(s.beta);
+    qa.gamma = to_dev(s.gamma);
+    for (int i = 0; i < 5; i++) qa.k[i] = to_dev(pk->k[i]);
+    memcpy(job->h_blind[g].b, blinders4[g], 4 * sizeof(Fr));
+    job->h_blind[g].rows_blinded = 4;
+  }
+  upload_args(job, job->d_quot, job->h_quot);
+  upload_args(job, job->d_blind, job->h_blind);
   // coset evaluations of the 5 wire polys, PI and z on the 8n domain (selectors / sigmas are cached in the pk)
-  ntt_device(ctx, pk->log_n + 3, job->polys, n + 3, NP, job->coset, m, job->ntt_tmp, 7, false, true);
-  QuotArgs qa;
-  qa.alpha = to_dev(job->alpha);
-  qa.alpha2 = to_dev(job->alpha.sqr());
-  qa.beta = to_dev(job->beta);
-  qa.gamma = to_dev(job->gamma);
-  for (int i = 0; i < 5; i++) qa.k[i] = to_dev(pk->k[i]);
-  qa.zh_inv = pk->zh_inv;
-  quotient_evals(ctx, job->coset, pk->sel_coset, pk->sig_coset, pk->xs, pk->l1inv, m, qa, job->t);
-  ntt_device(ctx, pk->log_n + 3, job->t, m, m, job->t, m, job->ntt_tmp, 1, true, true);
-  BlindArgs ba;
-  memcpy(ba.b, blinders4, 4 * sizeof(Fr));
-  ba.rows_blinded = 4;
-  split_quotient(ctx, job->t, n, m, job->split, NP, ba, job->flag);
-  msm_device(ctx, pk->srs, 0, job->split, n + 3, NP, 5, true, job->comms_dev, ctx->latency_mode);
-  uint8_t* pin = static_cast<uint8_t*>(ctx->pinned);
-  CAPGPU_CUDA(cudaMemcpyAsync(pin + 1024, job->flag, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  ntt_device(ctx, pk->log_n + 3, job->polys, n + 3, NP, job->coset, m, job->ntt_tmp, 7 * G, false, true);
+  quotient_evals(ctx, job->coset, pk->sel_coset, pk->sig_coset, pk->xs, pk->l1inv, pk->zh_inv, m, G, job->d_quot, job->t);
+  ntt_device(ctx, pk->log_n + 3, job->t, m, m, job->t, m, job->ntt_tmp, G, true, true);
+  split_quotient(ctx, job->t, n, m, G, job->split, NP, job->d_blind, job->flag);
+  msm_device(ctx, pk->srs, 0, job->split, n + 3, NP, 5 * G, true, job->comms_dev, ctx->latency_mode);
+  CAPGPU_CUDA(cudaMemcpyAsync(job->h_flag, job->flag, G * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   read_points(job, 5, split_comms);
-  uint32_t flag;
-  memcpy(&flag, pin + 1024, sizeof flag);
-  if (flag) throw CodeError{CAPGPU_ERR_DEGREE};
+  for (int g = 0; g < G; g++) status[g] = job->h_flag[g] ? CAPGPU_ERR_DEGREE : CAPGPU_OK;
   job->round = 4;
 }
 
-void round4(capgpu_job* job, const uint64_t* zeta, uint64_t* evals_out) {
+void round4(capgpu_job* job, const uint64_t* const* zeta, uint64_t* const* evals_out) {
   if (job->round != 4) throw CodeError{CAPGPU_ERR_STATE};
+  NvtxRange nv("capgpu round 4: evaluations");
   capgpu_ctx* ctx = job->ctx;
   const capgpu_pk* pk = job->pk;
   const size_t n = job->n, NP = job->NP;
-  job->zeta = HFr::from_limbs(zeta);
-  HFr zeta_w = job->zeta * host_omega(pk->log_n);
-  EvalArgs ea;
-  for (int i = 0; i < 5; i++) { ea.poly[i] = job->polys + (size_t)i * NP; ea.len[i] = n + 2; ea.x[i] = to_dev(job->zeta); }
-  for (int i = 0; i < 4; i++) { ea.poly[5 + i] = pk->sig_coef + (size_t)i * n; ea.len[5 + i] = n; ea.x[5 + i] = to_dev(job->zeta); }
-  ea.poly[9] = job->polys + 6 * NP; ea.len[9] = n + 3; ea.x[9] = to_dev(zeta_w);
-  evaluate(ctx, ea, 10, job->evals_dev, job->eval_scratch);
-  CAPGPU_CUDA(cudaMemcpyAsync(ctx->pinned, job->evals_dev, 10 * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
+  const int G = job->G;
+  const HFr omega = host_omega(pk->log_n);
+  for (int g = 0; g < G; g++) {
+    ProofState& s = job->st[g];
+    s.zeta = HFr::from_limbs(zeta[g]);
+    HFr zeta_w = s.zeta * omega;
+    EvalArgs& ea = job->h_eval[g];
+    for (int i = 0; i < 5; i++) { ea.poly[i] = job->polys + ((size_t)i * G + g) * NP; ea.len[i] = n + 2; ea.x[i] = to_dev(s.zeta); }
+    for (int i = 0; i < 4; i++) { ea.poly[5 + i] = pk->sig_coef + (size_t)i * n; ea.len[5 + i] = n; ea.x[5 + i] = to_dev(s.zeta); }
+    ea.poly[9] = job->polys + ((size_t)6 * G + g) * NP; ea.len[9] = n + 3; ea.x[9] = to_dev(zeta_w);
+  }
+  upload_args(job, job->d_eval, job->h_eval);
+  evaluate(ctx, job->d_eval, 10, G, job->evals_dev, job->eval_scratch);
+  CAPGPU_CUDA(cudaMemcpyAsync(job->h_evals, job->evals_dev, (size_t)G * 16 * sizeof(Fr), cudaMemcpyDeviceToHost, ctx->stream));
   ctx_wait(ctx);
-  memcpy(evals_out, ctx->pinned, 10 * sizeof(Fr));
-  for (int i = 0; i < 10; i++) job->evals[i] = HFr::from_limbs(evals_out + 4 * i);
+  for (int g = 0; g < G; g++) {
+    memcpy(evals_out[g], job->h_evals + (size_t)g * 16, 10 * sizeof(Fr));
+    for (int i = 0; i < 10; i++) job->st[g].evals[i] = HFr::from_limbs(evals_out[g] + 4 * i);
+  }
   job->round = 5;
 }
 
-void round5(capgpu_job* job, const uint64_t* v_in, uint64_t* opening_comms) {
+void round5(capgpu_job* job, const uint64_t* const* v_in, uint64_t* const* opening_comms) {
   if (job->round != 5) throw CodeError{CAPGPU_ERR_STATE};
+  NvtxRange nv("capgpu round 5: linearisation + opening proofs");
   capgpu_ctx* ctx = job->ctx;
   const capgpu_pk* pk = job->pk;
   const size_t n = job->n, NP = job->NP;
-  job->v = HFr::from_limbs(v_in);
-  const HFr* w = job->evals;           // wires_evals[5]
-  const HFr* se = job->evals + 5;      // wire_sigma_evals[4]
-  const HFr zw = job->evals[9];        // perm_next_eval
-  const HFr &alpha = job->alpha, &beta = job->beta, &gamma = job->gamma, &zeta = job->zeta;
+  const int G = job->G;
   const HFr one = HFr::one();
-  HFr zh = zeta.pow_u64(n) - one;
-  HFr l1 = zh * (HFr::from_u64(n) * (zeta - one)).inv();
-  LinArgs la;
-  la.polys = job->polys; la.split = job->split; la.sel = pk->sel_coef; la.sig = pk->sig_coef;
-  la.pstride = NP; la.n = n; la.len = n + 3;
-  HFr w01 = w[0] * w[1], w23 = w[2] * w[3];
-  auto p5 = [](const HFr& x) { HFr x2 = x.sqr(); return x2.sqr() * x; };
-  HFr sel[13] = {w[0], w[1], w[2], w[3], w01, w23, p5(w[0]), p5(w[1]), p5(w[2]), p5(w[3]), w[4].neg(), one, w01 * w23 * w[4]};
-  for (int s = 0; s < 13; s++) la.cs_sel[s] = to_dev(sel[s]);
-  HFr cz = alpha;
-  HFr bz = beta * zeta;
-  for (int j = 0; j < 5; j++) cz = cz * (w[j] + pk->k[j] * bz + gamma);
-  cz = cz + alpha.sqr() * l1;
-  la.cz = to_dev(cz);
-  HFr cs = alpha * beta * zw;
-  for (int j = 0; j < 4; j++) cs = cs * (w[j] + beta * se[j] + gamma);
-  la.csig = to_dev(cs.neg());
-  HFr zn2 = (zh + one) * zeta * zeta;
-  HFr c = one;
-  for (int i = 0; i < 5; i++) { la.ct[i] = to_dev((zh * c).neg()); c = c * zn2; }
-  HFr vp = job->v;
-  for (int i = 0; i < 9; i++) { la.vp[i] = to_dev(vp); vp = vp * job->v; }
-  lin_batch(ctx, la, job->lin, job->batch);
-  DivArgs da;
-  const HFr zeta_w = zeta * host_omega(pk->log_n);
-  da.src[0] = job->batch; da.dst[0] = job->open; da.len[0] = n + 3; da.x[0] = to_dev(zeta); da.xinv[0] = to_dev(zeta.inv());
-  da.src[1] = job->polys + 6 * NP; da.dst[1] = job->shifted; da.len[1] = n + 3; da.x[1] = to_dev(zeta_w); da.xinv[1] = to_dev(zeta_w.inv());
-  divide_linear(ctx, da, 2, job->div_scratch, job->div_tmax);
-  // open and shifted are adjacent rows of stride NP
-  msm_device(ctx, pk->srs, 0, job->open, n + 2, NP, 2, true, job->comms_dev, ctx->latency_mode);
+  const HFr omega = host_omega(pk->log_n);
+  const HFr n_mont = HFr::from_u64(n);
+  for (int g = 0; g < G; g++) {
+    ProofState& s = job->st[g];
+    s.v = HFr::from_limbs(v_in[g]);
+    const HFr* w = s.evals;           // wires_evals[5]
+    const HFr* se = s.evals + 5;      // wire_sigma_evals[4]
+    const HFr zw = s.evals[9];        // perm_next_eval
+    const HFr &alpha = s.alpha, &beta = s.beta, &gamma = s.gamma, &zeta = s.zeta;
+    HFr zh = zeta.pow_u64(n) - one;
+    HFr l1 = zh * (n_mont * (zeta - one)).inv();
+    LinArgs& la = job->h_lin[g];
+    la.polys = job->polys + (size_t)g * NP;
+    la.split = job->split + (size_t)g * NP;
+    la.rstride = (size_t)G * NP;
+    HFr w01 = w[0] * w[1], w23 = w[2] * w[3];
+    auto p5 = [](const HFr& x) { HFr x2 = x.sqr(); return x2.sqr() * x; };
+    HFr sel[13] = {w[0], w[1], w[2], w[3], w01, w23, p5(w[0]), p5(w[1]), p5(w[2]), p5(w[3]), w[4].neg(), one, w01 * w23 * w[4]};
+    for (int i = 0; i < 13; i++) la.cs_sel[i] = to_dev(sel[i]);
+    HFr cz = alpha;
+    HFr bz = beta * zeta;
+    for (int j = 0; j < 5; j++) cz = cz * (w[j] + pk->k[j] * bz + gamma);
+    cz = cz + alpha.sqr() * l1;
+    la.cz = to_dev(cz);
+    HFr cs = alpha * beta * zw;
+    for (int j = 0; j < 4; j++) cs = cs * (w[j] + beta * se[j] + gamma);
+    la.csig = to_dev(cs.neg());
+    HFr zn2 = (zh + one) * zeta * zeta;
+    HFr c = one;
+    for (int i = 0; i < 5; i++) { la.ct[i] = to_dev((zh * c).neg()); c = c * zn2; }
+    HFr vp = s.v;
+    for (int i = 0; i < 9; i++) { la.vp[i] = to_dev(vp); vp = vp * s.v; }
+    DivArgs& da = job->h_div[g];
+    const HFr zeta_w = zeta * omega;
+    da.src[0] = job->batch + (size_t)g * NP; da.dst[0] = job->open + (size_t)g * NP; da.len[0] = n + 3;
+    da.x[0] = to_dev(zeta); da.xinv[0] = to_dev(zeta.inv());
+    da.src[1] = job->polys + ((size_t)6 * G + g) * NP; da.dst[1] = job->open + ((size_t)G + g) * NP; da.len[1] = n + 3;
+    da.x[1] = to_dev(zeta_w); da.xinv[1] = to_dev(zeta_w.inv());
+  }
+  upload_args(job, job->d_lin, job->h_lin);
+  upload_args(job, job->d_div, job->h_div);
+  lin_batch(ctx, job->d_lin, pk->sel_coef, pk->sig_coef, n, n + 3, G, job->lin, job->batch, NP);
+  divide_linear(ctx, job->d_div, 2, G, n + 3, job->div_scratch, job->div_tmax);
+  // rows (0, g) = opening quotient, (1, g) = shifted opening quotient
+  msm_device(ctx, pk->srs, 0, job->open, n + 2, NP, 2 * G, true, job->comms_dev, ctx->latency_mode);
   read_points(job, 2, opening_comms);
   job->round = 6;
 }
@@ -337,16 +449,19 @@ void pk_free(capgpu_pk* pk) {
   Fr* ptrs[] = {pk->sel_coef, pk->sig_coef, pk->sig_eval, pk->sel_coset, pk->sig_coset, pk->xs, pk->l1inv, pk->zh_inv, pk->omega_n};
   for (Fr* p : ptrs) if (p) cudaFree(p);
   if (pk->lag) capgpu_srs_destroy(pk->lag);
+  if (pk->owned_srs) capgpu_srs_destroy(pk->owned_srs);
   delete pk;
 }
 
 }  // namespace
 
 // ---- C ABI ------------------------------------------------------------------------------
-extern "C" int capgpu_pk_upload(capgpu_ctx* ctx, const capgpu_srs* srs, unsigned log_n, size_t num_inputs, const uint64_t* selectors,
+namespace capgpu {
+
+// shared by capgpu_pk_upload and the CanonicalSerialize loader (formats.cu)
+int pk_create_from_coefficients(capgpu_ctx* ctx, const capgpu_srs* srs, unsigned log_n, size_t num_inputs, const uint64_t* selectors,
                                 const uint64_t* sigmas, const uint64_t* k, const uint64_t* selector_comms_xy,
                                 const uint64_t* sigma_comms_xy, capgpu_pk** out) {
-  if (!ctx || !srs || !selectors || !sigmas || !k || !selector_comms_xy || !sigma_comms_xy || !out) return CAPGPU_ERR_ARG;
   *out = nullptr;
   capgpu_pk* pk = nullptr;
   int rc = guarded(ctx, [&] {
@@ -365,6 +480,15 @@ extern "C" int capgpu_pk_upload(capgpu_ctx* ctx, const capgpu_srs* srs, unsigned
   if (rc != CAPGPU_OK) { pk_free(pk); return rc; }
   *out = pk;
   return CAPGPU_OK;
+}
+
+}  // namespace capgpu
+
+extern "C" int capgpu_pk_upload(capgpu_ctx* ctx, const capgpu_srs* srs, unsigned log_n, size_t num_inputs, const uint64_t* selectors,
+                                const uint64_t* sigmas, const uint64_t* k, const uint64_t* selector_comms_xy,
+                                const uint64_t* sigma_comms_xy, capgpu_pk** out) {
+  if (!ctx || !srs || !selectors || !sigmas || !k || !selector_comms_xy || !sigma_comms_xy || !out) return CAPGPU_ERR_ARG;
+  return pk_create_from_coefficients(ctx, srs, log_n, num_inputs, selectors, sigmas, k, selector_comms_xy, sigma_comms_xy, out);
 }
 
 extern "C" int capgpu_preprocess(capgpu_ctx* ctx, const capgpu_srs* srs, unsigned log_n, size_t num_inputs,
@@ -386,10 +510,8 @@ extern "C" int capgpu_preprocess(capgpu_ctx* ctx, const capgpu_srs* srs, unsigne
     ntt_device(ctx, log_n, pk->sig_coef, n, n, pk->sig_coef, n, ctx->ntt_tmp.as<Fr>(), 5, true, false);
     ctx->msm_out.reserve(18 * sizeof(G1Affine));
     G1Affine* outp = ctx->msm_out.as<G1Affine>();
-    for (int s = 0; s < 13; s += 5) {
-      int cnt = 13 - s < 5 ? 13 - s : 5;
-      msm_device(ctx, srs, 0, pk->sel_coef + (size_t)s * n, n, n, cnt, true, outp + s);
-    }
+    // the selector and sigma coefficient blocks are separate allocations: two batched MSMs
+    msm_device(ctx, srs, 0, pk->sel_coef, n, n, 13, true, outp);
     msm_device(ctx, srs, 0, pk->sig_coef, n, n, 5, true, outp + 13);
     CAPGPU_CUDA(cudaMemcpyAsync(pk->sel_comms, outp, 13 * sizeof(G1Affine), cudaMemcpyDeviceToHost, ctx->stream));
     CAPGPU_CUDA(cudaMemcpyAsync(pk->sig_comms, outp + 13, 5 * sizeof(G1Affine), cudaMemcpyDeviceToHost, ctx->stream));
@@ -416,6 +538,14 @@ extern "C" int capgpu_pk_export(capgpu_ctx* ctx, const capgpu_pk* pk, uint64_t* 
 
 extern "C" void capgpu_pk_destroy(capgpu_pk* pk) { pk_free(pk); }
 
+extern "C" int capgpu_pk_info(const capgpu_pk* pk, unsigned* log_n, size_t* num_inputs, uint64_t* k) {
+  if (!pk) return CAPGPU_ERR_ARG;
+  if (log_n) *log_n = pk->log_n;
+  if (num_inputs) *num_inputs = pk->num_inputs;
+  if (k) for (int i = 0; i < 5; i++) memcpy(k + 4 * i, pk->k[i].v, 32);
+  return CAPGPU_OK;
+}
+
 extern "C" int capgpu_pk_lagrange(capgpu_pk* pk, int enable) {
   if (!pk) return CAPGPU_ERR_ARG;
   if (enable && !pk->lag) return CAPGPU_ERR_STATE;
@@ -433,9 +563,10 @@ extern "C" int capgpu_job_begin(capgpu_ctx* ctx, const capgpu_pk* pk, const uint
   if (!ctx || !pk || !wires || !out || (!pub_inputs && pk->num_inputs)) return CAPGPU_ERR_ARG;
   *out = nullptr;
   return guarded(ctx, [&] {
-    capgpu_job* job = job_acquire(ctx, pk);
+    capgpu_job* job = job_acquire(ctx, pk, 1);
     try {
-      job_begin(job, wires, pub_inputs);
+      NoteIn in{wires, false, pub_inputs, nullptr, nullptr, 0};
+      job_begin(job, &in);
     } catch (...) {
       job->busy = false;
       throw;
@@ -444,36 +575,128 @@ extern "C" int capgpu_job_begin(capgpu_ctx* ctx, const capgpu_pk* pk, const uint
   });
 }
 
-#define CAPGPU_JOB_GUARD(job, body)                    \
-  if (!(job) || !(job)->busy) return CAPGPU_ERR_STATE; \
-  return guarded((job)->ctx, [&] { body; });
+// A round that fails (CUDA error, wrong quotient degree, out-of-order call) releases the job: the
+// context is immediately usable for a new capgpu_job_begin / capgpu_prove, and the failed job
+// handle only accepts capgpu_job_end (a no-op then).
+template <class F>
+static int job_round(capgpu_job* job, F&& body) {
+  if (!job || !job->busy) return CAPGPU_ERR_STATE;
+  int rc = guarded(job->ctx, body);
+  if (rc != CAPGPU_OK && rc != CAPGPU_ERR_STATE) job->busy = false;
+  return rc;
+}
 
 extern "C" int capgpu_job_round1(capgpu_job* job, const uint64_t* blinders10, uint64_t* wire_comms_xy) {
   if (!blinders10 || !wire_comms_xy) return CAPGPU_ERR_ARG;
-  CAPGPU_JOB_GUARD(job, round1(job, blinders10, wire_comms_xy));
+  return job_round(job, [&] { round1(job, &blinders10, &wire_comms_xy); });
 }
 extern "C" int capgpu_job_round2(capgpu_job* job, const uint64_t* beta, const uint64_t* gamma, const uint64_t* blinders3, uint64_t* z_comm_xy) {
   if (!beta || !gamma || !blinders3 || !z_comm_xy) return CAPGPU_ERR_ARG;
-  CAPGPU_JOB_GUARD(job, round2(job, beta, gamma, blinders3, z_comm_xy));
+  return job_round(job, [&] { round2(job, &beta, &gamma, &blinders3, &z_comm_xy); });
 }
 extern "C" int capgpu_job_round3(capgpu_job* job, const uint64_t* alpha, const uint64_t* blinders4, uint64_t* split_comms_xy) {
   if (!alpha || !blinders4 || !split_comms_xy) return CAPGPU_ERR_ARG;
-  CAPGPU_JOB_GUARD(job, round3(job, alpha, blinders4, split_comms_xy));
+  return job_round(job, [&] {
+    int st = CAPGPU_OK;
+    round3(job, &alpha, &blinders4, &split_comms_xy, &st);
+    if (st != CAPGPU_OK) throw CodeError{st};
+  });
 }
 extern "C" int capgpu_job_round4(capgpu_job* job, const uint64_t* zeta, uint64_t* evals) {
   if (!zeta || !evals) return CAPGPU_ERR_ARG;
-  CAPGPU_JOB_GUARD(job, round4(job, zeta, evals));
+  return job_round(job, [&] { round4(job, &zeta, &evals); });
 }
 extern "C" int capgpu_job_round5(capgpu_job* job, const uint64_t* v, uint64_t* opening_comms_xy) {
   if (!v || !opening_comms_xy) return CAPGPU_ERR_ARG;
-  CAPGPU_JOB_GUARD(job, round5(job, v, opening_comms_xy));
+  return job_round(job, [&] { round5(job, &v, &opening_comms_xy); });
 }
 extern "C" void capgpu_job_end(capgpu_job* job) {
   if (job) job->busy = false;
 }
 
+// ---- whole proofs: one lockstep group --------------------------------------------------------
+namespace capgpu {
+
+// Proves notes[0..G) in lockstep on ctx.  status[g]: per-proof result (CAPGPU_ERR_DEGREE for an
+// unsatisfied circuit; the rest of the group still completes).  Throws on CUDA / argument errors
+// (the whole group fails).  `inputs_consumed` (optional) is called once the wire values have been
+// read from the callers' buffers (end of round 1).
+void prove_group(capgpu_ctx* ctx, const capgpu_pk* pk, int G, const NoteIn* notes, capgpu_proof* const* out, int* status,
+                 const std::function<void()>& inputs_consumed) {
+  capgpu_job* job = job_acquire(ctx, pk, G);
+  struct Release { capgpu_job* j; ~Release() { j->busy = false; } } release{job};
+  job_begin(job, notes);
+  std::vector<SolidityTranscript> tr(G);
+  std::vector<HFr> ch(2 * G);
+  std::vector<const uint64_t*> p0(G), p1(G), p2(G);
+  std::vector<uint64_t*> o0(G);
+  for (int g = 0; g < G; g++) {
+    if (notes[g].ext_msg_len) tr[g].append_message(notes[g].ext_msg, notes[g].ext_msg_len);
+    tr[g].append_message(pk->vk_bytes.data(), pk->vk_bytes.size());
+    for (size_t i = 0; i < pk->num_inputs; i++) tr[g].append_field(HFr::from_limbs(notes[g].pub_inputs + 4 * i));
+    status[g] = CAPGPU_OK;
+  }
+  // Round 1
+  for (int g = 0; g < G; g++) { p0[g] = notes[g].blinders; o0[g] = &out[g]->wires_poly_comms[0][0]; }
+  round1(job, p0.data(), o0.data());
+  if (inputs_consumed) inputs_consumed();
+  // Round 2
+  for (int g = 0; g < G; g++) {
+    for (int i = 0; i < 5; i++) tr[g].append_commitment(out[g]->wires_poly_comms[i]);
+    ch[2 * g] = tr[g].get_and_append_challenge();
+    ch[2 * g + 1] = tr[g].get_and_append_challenge();
+    p0[g] = ch[2 * g].v; p1[g] = ch[2 * g + 1].v; p2[g] = notes[g].blinders + 4 * 10;
+    o0[g] = out[g]->prod_perm_poly_comm;
+  }
+  round2(job, p0.data(), p1.data(), p2.data(), o0.data());
+  // Round 3
+  for (int g = 0; g < G; g++) {
+    tr[g].append_commitment(out[g]->prod_perm_poly_comm);
+    ch[g] = tr[g].get_and_append_challenge();
+    p0[g] = ch[g].v; p1[g] = notes[g].blinders + 4 * 13;
+    o0[g] = &out[g]->split_quot_poly_comms[0][0];
+  }
+  round3(job, p0.data(), p1.data(), o0.data(), status);
+  // Round 4
+  std::vector<uint64_t> evals((size_t)G * 40);
+  for (int g = 0; g < G; g++) {
+    for (int i = 0; i < 5; i++) tr[g].append_commitment(out[g]->split_quot_poly_comms[i]);
+    ch[g] = tr[g].get_and_append_challenge();
+    p0[g] = ch[g].v;
+    o0[g] = evals.data() + (size_t)g * 40;
+  }
+  round4(job, p0.data(), o0.data());
+  // Round 5
+  for (int g = 0; g < G; g++) {
+    const uint64_t* ev = evals.data() + (size_t)g * 40;
+    memcpy(out[g]->wires_evals, ev, 5 * 32);
+    memcpy(out[g]->wire_sigma_evals, ev + 20, 4 * 32);
+    memcpy(out[g]->perm_next_eval, ev + 36, 32);
+    for (int i = 0; i < 10; i++) tr[g].append_field(HFr::from_limbs(ev + 4 * i));
+    ch[g] = tr[g].get_and_append_challenge();
+    p0[g] = ch[g].v;
+  }
+  std::vector<uint64_t> open2((size_t)G * 16);
+  for (int g = 0; g < G; g++) o0[g] = open2.data() + (size_t)g * 16;
+  round5(job, p0.data(), o0.data());
+  for (int g = 0; g < G; g++) {
+    memcpy(out[g]->opening_proof, open2.data() + (size_t)g * 16, 64);
+    memcpy(out[g]->shifted_opening_proof, open2.data() + (size_t)g * 16 + 8, 64);
+  }
+}
+
+}  // namespace capgpu
+
 static int prove_impl(capgpu_ctx* ctx, const capgpu_pk* pk, const uint64_t* wires, bool wires_on_device, const uint64_t* pub_inputs,
-                      const uint64_t* blinders, const uint8_t* ext_msg, size_t ext_msg_len, capgpu_proof* out);
+                      const uint64_t* blinders, const uint8_t* ext_msg, size_t ext_msg_len, capgpu_proof* out) {
+  if (!ctx || !pk || !wires || !blinders || !out || (!pub_inputs && pk->num_inputs) || (!ext_msg && ext_msg_len)) return CAPGPU_ERR_ARG;
+  int status = CAPGPU_OK;
+  int rc = guarded(ctx, [&] {
+    NoteIn in{wires, wires_on_device, pub_inputs, blinders, ext_msg, ext_msg_len};
+    prove_group(ctx, pk, 1, &in, &out, &status, nullptr);
+  });
+  return rc != CAPGPU_OK ? rc : status;
+}
 
 extern "C" int capgpu_prove(capgpu_ctx* ctx, const capgpu_pk* pk, const uint64_t* wires, const uint64_t* pub_inputs,
                             const uint64_t* blinders, const uint8_t* ext_msg, size_t ext_msg_len, capgpu_proof* out) {
@@ -485,69 +708,57 @@ extern "C" int capgpu_prove_dev(capgpu_ctx* ctx, const capgpu_pk* pk, const void
   return prove_impl(ctx, pk, (const uint64_t*)d_wires, true, pub_inputs, blinders, ext_msg, ext_msg_len, out);
 }
 
-static int prove_impl(capgpu_ctx* ctx, const capgpu_pk* pk, const uint64_t* wires, bool wires_on_device, const uint64_t* pub_inputs,
-                      const uint64_t* blinders, const uint8_t* ext_msg, size_t ext_msg_len, capgpu_proof* out) {
-  if (!ctx || !pk || !wires || !blinders || !out || (!pub_inputs && pk->num_inputs) || (!ext_msg && ext_msg_len)) return CAPGPU_ERR_ARG;
-  return guarded(ctx, [&] {
-    capgpu_job* job = job_acquire(ctx, pk);
-    struct Release { capgpu_job* j; ~Release() { j->busy = false; } } release{job};
-    job_begin(job, wires, pub_inputs, wires_on_device);
-    SolidityTranscript tr;
-    if (ext_msg_len) tr.append_message(ext_msg, ext_msg_len);
-    tr.append_message(pk->vk_bytes.data(), pk->vk_bytes.size());
-    for (size_t i = 0; i < pk->num_inputs; i++) tr.append_field(HFr::from_limbs(pub_inputs + 4 * i));
-    // Round 1
-    round1(job, blinders, &out->wires_poly_comms[0][0]);
-    for (int i = 0; i < 5; i++) tr.append_commitment(out->wires_poly_comms[i]);
-    // Round 2
-    HFr beta = tr.get_and_append_challenge();
-    HFr gamma = tr.get_and_append_challenge();
-    round2(job, beta.v, gamma.v, blinders + 4 * 10, out->prod_perm_poly_comm);
-    tr.append_commitment(out->prod_perm_poly_comm);
-    // Round 3
-    HFr alpha = tr.get_and_append_challenge();
-    round3(job, alpha.v, blinders + 4 * 13, &out->split_quot_poly_comms[0][0]);
-    for (int i = 0; i < 5; i++) tr.append_commitment(out->split_quot_poly_comms[i]);
-    // Round 4
-    HFr zeta = tr.get_and_append_challenge();
-    uint64_t evals[40];
-    round4(job, zeta.v, evals);
-    memcpy(out->wires_evals, evals, 5 * 32);
-    memcpy(out->wire_sigma_evals, evals + 20, 4 * 32);
-    memcpy(out->perm_next_eval, evals + 36, 32);
-    for (int i = 0; i < 10; i++) tr.append_field(HFr::from_limbs(evals + 4 * i));
-    // Round 5
-    HFr v = tr.get_and_append_challenge();
-    uint64_t open2[16];
-    round5(job, v.v, open2);
-    memcpy(out->opening_proof, open2, 64);
-    memcpy(out->shifted_opening_proof, open2 + 8, 64);
-  });
+extern "C" int capgpu_ctx_set_group(capgpu_ctx* ctx, int group) {
+  if (!ctx || group < 1 || group > CAPGPU_MAX_GROUP) return CAPGPU_ERR_ARG;
+  ctx->group = group;
+  return CAPGPU_OK;
 }
 
 // Batch of independent notes over one proving key: the B200 counterpart of the reference's rayon
 // loop over builders (/root/reference/src/utils/params_builder.rs:195-233).  One worker thread per
-// context pulls note indices from a shared counter; each context's stream carries one proof at a
-// time, so latency-bound kernels of one proof overlap with throughput-bound kernels of another.
-extern "C" int capgpu_prove_batch(capgpu_ctx* const* ctxs, size_t n_ctxs, const capgpu_pk* pk, size_t count,
-                                  const uint64_t* const* wires, const uint64_t* const* pub_inputs, const uint64_t* const* blinders,
-                                  const uint8_t* const* ext_msgs, const size_t* ext_msg_lens, capgpu_proof* out, int* status) {
+// context pulls GROUPS of notes from a shared counter and proves each group in lockstep; two to
+// four contexts per GPU keep it busy while one group waits on a host round trip.
+static int prove_batch_impl(capgpu_ctx* const* ctxs, size_t n_ctxs, const capgpu_pk* pk, size_t count, const uint64_t* const* wires,
+                            bool wires_on_device, const uint64_t* const* pub_inputs, const uint64_t* const* blinders,
+                            const uint8_t* const* ext_msgs, const size_t* ext_msg_lens, capgpu_proof* out, int* status) {
   if (!ctxs || !n_ctxs || !pk || (count && (!wires || !blinders || !out))) return CAPGPU_ERR_ARG;
+  if (!pub_inputs && pk->num_inputs && count) return CAPGPU_ERR_ARG;
   for (size_t i = 0; i < n_ctxs; i++) if (!ctxs[i]) return CAPGPU_ERR_ARG;
-  std::atomic<size_t> next{0};
+  for (size_t i = 0; i < count; i++)
+    if (!wires[i] || !blinders[i] || (pk->num_inputs && !pub_inputs[i])) return CAPGPU_ERR_ARG;
+  std::mutex mu;
+  size_t next = 0;
   std::atomic<int> first_error{CAPGPU_OK};
+  // groups are dealt so that every context gets work: never more than an even share of what is left
   auto worker = [&](capgpu_ctx* ctx) {
     for (;;) {
-      size_t i = next.fetch_add(1);
-      if (i >= count) break;
-      const uint64_t* pi = pub_inputs ? pub_inputs[i] : nullptr;
-      const uint8_t* msg = ext_msgs ? ext_msgs[i] : nullptr;
-      size_t len = (ext_msgs && ext_msg_lens) ? ext_msg_lens[i] : 0;
-      int rc = capgpu_prove(ctx, pk, wires[i], pi, blinders[i], msg, len, &out[i]);
-      if (status) status[i] = rc;
-      if (rc != CAPGPU_OK) {
-        int expected = CAPGPU_OK;
-        first_error.compare_exchange_strong(expected, rc);
+      size_t i0, take;
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        if (next >= count) break;
+        const size_t left = count - next, share = (left + n_ctxs - 1) / n_ctxs;
+        take = (size_t)ctx->group < share ? (size_t)ctx->group : share;
+        i0 = next;
+        next += take;
+      }
+      const int g_n = (int)take;
+      std::vector<NoteIn> notes(g_n);
+      std::vector<capgpu_proof*> outs(g_n);
+      std::vector<int> st(g_n, CAPGPU_OK);
+      for (int g = 0; g < g_n; g++) {
+        const size_t i = i0 + g;
+        notes[g] = NoteIn{wires[i], wires_on_device, pub_inputs ? pub_inputs[i] : nullptr, blinders[i], ext_msgs ? ext_msgs[i] : nullptr,
+                          (ext_msgs && ext_msg_lens && ext_msgs[i]) ? ext_msg_lens[i] : 0};
+        outs[g] = &out[i];
+      }
+      int rc = guarded(ctx, [&] { prove_group(ctx, pk, g_n, notes.data(), outs.data(), st.data(), nullptr); });
+      for (int g = 0; g < g_n; g++) {
+        const int code = rc != CAPGPU_OK ? rc : st[g];
+        if (status) status[i0 + g] = code;
+        if (code != CAPGPU_OK) {
+          int expected = CAPGPU_OK;
+          first_error.compare_exchange_strong(expected, code);
+        }
       }
     }
   };
@@ -558,25 +769,234 @@ extern "C" int capgpu_prove_batch(capgpu_ctx* const* ctxs, size_t n_ctxs, const 
   return first_error.load();
 }
 
+extern "C" int capgpu_prove_batch(capgpu_ctx* const* ctxs, size_t n_ctxs, const capgpu_pk* pk, size_t count,
+                                  const uint64_t* const* wires, const uint64_t* const* pub_inputs, const uint64_t* const* blinders,
+                                  const uint8_t* const* ext_msgs, const size_t* ext_msg_lens, capgpu_proof* out, int* status) {
+  return prove_batch_impl(ctxs, n_ctxs, pk, count, wires, false, pub_inputs, blinders, ext_msgs, ext_msg_lens, out, status);
+}
+
+extern "C" int capgpu_prove_batch_dev(capgpu_ctx* const* ctxs, size_t n_ctxs, const capgpu_pk* pk, size_t count,
+                                      const void* const* d_wires, const uint64_t* const* pub_inputs, const uint64_t* const* blinders,
+                                      const uint8_t* const* ext_msgs, const size_t* ext_msg_lens, capgpu_proof* out, int* status) {
+  return prove_batch_impl(ctxs, n_ctxs, pk, count, reinterpret_cast<const uint64_t* const*>(d_wires), true, pub_inputs, blinders,
+                          ext_msgs, ext_msg_lens, out, status);
+}
+
+// ---- asynchronous proving queue ----------------------------------------------------------------
+// the host overlaps witness generation for note k+1 (TransferCircuit::build,
+// /root/reference/src/proof/transfer.rs:167-177) with proving of note k (transfer.rs:181).
+// capgpu_submit copies the note's wire values into a slot of a pinned staging ring (so the
+// caller's pageable Vec<Fr> can be dropped at once) and returns a ticket; one worker thread per
+// context collects up to `group` pending notes and proves them in lockstep; capgpu_poll /
+// capgpu_wait deliver the proof.
+struct capgpu_queue {
+  std::vector<capgpu_ctx*> ctxs;
+  const capgpu_pk* pk = nullptr;
+  size_t n = 0, num_inputs = 0;
+  struct Note {
+    uint64_t ticket = 0;
+    int slot = -1;
+    std::vector<uint64_t> pub, blinders;
+    std::vector<uint8_t> ext;
+    int state = 0;  // 0 queued, 1 running, 2 done
+    int status = CAPGPU_OK;
+    capgpu_proof proof;
+  };
+  std::mutex mu;
+  std::condition_variable cv_work, cv_done, cv_slot;
+  std::deque<Note*> pending;
+  std::unordered_map<uint64_t, Note*> notes;
+  uint64_t next_ticket = 1;
+  char* ring = nullptr;
+  size_t slot_bytes = 0;
+  std::vector<int> free_slots;
+  bool stop = false;
+  unsigned linger_us = 300;
+  std::vector<std::thread> workers;
+  // statistics
+  uint64_t submitted = 0, completed = 0, groups = 0;
+  double copy_ms = 0, wait_slot_ms = 0;
+
+  void run(capgpu_ctx* ctx) {
+    const size_t G = (size_t)ctx->group;
+    for (;;) {
+      std::vector<Note*> grp;
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv_work.wait(lk, [&] { return stop || !pending.empty(); });
+        if (stop && pending.empty()) return;
+        // linger briefly for a fuller group while notes are still arriving
+        if (pending.size() < G && !stop) {
+          auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(linger_us);
+          cv_work.wait_until(lk, deadline, [&] { return stop || pending.size() >= G; });
+        }
+        // leave work for the other contexts: never more than an even share of what is pending
+        const size_t share = (pending.size() + ctxs.size() - 1) / ctxs.size();
+        const size_t take = share < G ? share : G;
+        for (size_t i = 0; i < take; i++) { grp.push_back(pending.front()); pending.pop_front(); grp.back()->state = 1; }
+        groups++;
+      }
+      if (grp.empty()) continue;
+      const int g_n = (int)grp.size();
+      std::vector<NoteIn> in(g_n);
+      std::vector<capgpu_proof*> outs(g_n);
+      std::vector<int> st(g_n, CAPGPU_OK);
+      for (int g = 0; g < g_n; g++) {
+        Note* nt = grp[g];
+        in[g] = NoteIn{reinterpret_cast<const uint64_t*>(ring + (size_t)nt->slot * slot_bytes), false,
+                       nt->pub.empty() ? nullptr : nt->pub.data(), nt->blinders.data(), nt->ext.empty() ? nullptr : nt->ext.data(),
+                       nt->ext.size()};
+        outs[g] = &nt->proof;
+      }
+      bool released = false;
+      auto release_slots = [&] {
+        if (released) return;
+        released = true;
+        std::lock_guard<std::mutex> lk(mu);
+        for (Note* nt : grp) { free_slots.push_back(nt->slot); nt->slot = -1; }
+        cv_slot.notify_all();
+      };
+      int rc = guarded(ctx, [&] { prove_group(ctx, pk, g_n, in.data(), outs.data(), st.data(), release_slots); });
+      release_slots();
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        for (int g = 0; g < g_n; g++) {
+          grp[g]->status = rc != CAPGPU_OK ? rc : st[g];
+          grp[g]->state = 2;
+          completed++;
+        }
+      }
+      cv_done.notify_all();
+    }
+  }
+};
+
+extern "C" int capgpu_queue_create(capgpu_ctx* const* ctxs, size_t n_ctxs, const capgpu_pk* pk, size_t ring_slots, capgpu_queue** out) {
+  if (!ctxs || !n_ctxs || !pk || !out) return CAPGPU_ERR_ARG;
+  *out = nullptr;
+  for (size_t i = 0; i < n_ctxs; i++)
+    if (!ctxs[i] || ctxs[i]->device != pk->device) return CAPGPU_ERR_ARG;
+  capgpu_queue* q = new capgpu_queue();
+  q->pk = pk;
+  q->n = pk->n;
+  q->num_inputs = pk->num_inputs;
+  q->ctxs.assign(ctxs, ctxs + n_ctxs);
+  size_t groups = 0;
+  for (size_t i = 0; i < n_ctxs; i++) groups += (size_t)ctxs[i]->group;
+  if (ring_slots == 0) ring_slots = 2 * groups;  // one group in flight + one being filled, per context
+  q->slot_bytes = 5 * q->n * sizeof(Fr);
+  if (const char* e = getenv("CAPGPU_QUEUE_LINGER_US")) q->linger_us = (unsigned)atoi(e);
+  int rc = guarded(ctxs[0], [&] { CAPGPU_CUDA(cudaHostAlloc((void**)&q->ring, ring_slots * q->slot_bytes, cudaHostAllocPortable)); });
+  if (rc != CAPGPU_OK) { delete q; return rc; }
+  for (size_t s = ring_slots; s-- > 0;) q->free_slots.push_back((int)s);
+  for (size_t i = 0; i < n_ctxs; i++) q->workers.emplace_back([q, i] { q->run(q->ctxs[i]); });
+  *out = q;
+  return CAPGPU_OK;
+}
+
+extern "C" void capgpu_queue_destroy(capgpu_queue* q) {
+  if (!q) return;
+  {
+    std::lock_guard<std::mutex> lk(q->mu);
+    q->stop = true;
+  }
+  q->cv_work.notify_all();
+  for (auto& t : q->workers) t.join();
+  for (auto& kv : q->notes) delete kv.second;
+  if (q->ring) {
+    cudaSetDevice(q->pk->device);
+    cudaFreeHost(q->ring);
+  }
+  delete q;
+}
+
+extern "C" int capgpu_submit(capgpu_queue* q, const uint64_t* wires, const uint64_t* pub_inputs, const uint64_t* blinders,
+                             const uint8_t* ext_msg, size_t ext_msg_len, uint64_t* ticket) {
+  if (!q || !wires || !blinders || !ticket || (!pub_inputs && q->num_inputs) || (!ext_msg && ext_msg_len)) return CAPGPU_ERR_ARG;
+  auto* nt = new capgpu_queue::Note();
+  if (q->num_inputs) nt->pub.assign(pub_inputs, pub_inputs + 4 * q->num_inputs);
+  nt->blinders.assign(blinders, blinders + 4 * CAPGPU_NUM_BLINDERS);
+  if (ext_msg_len) nt->ext.assign(ext_msg, ext_msg + ext_msg_len);
+  auto t0 = std::chrono::steady_clock::now();
+  {
+    std::unique_lock<std::mutex> lk(q->mu);
+    if (q->stop) { delete nt; return CAPGPU_ERR_STATE; }
+    q->cv_slot.wait(lk, [&] { return !q->free_slots.empty(); });  // back-pressure: the ring is full
+    nt->slot = q->free_slots.back();
+    q->free_slots.pop_back();
+  }
+  auto t1 = std::chrono::steady_clock::now();
+  memcpy(q->ring + (size_t)nt->slot * q->slot_bytes, wires, q->slot_bytes);  // pageable -> pinned, on the caller's thread
+  auto t2 = std::chrono::steady_clock::now();
+  {
+    std::lock_guard<std::mutex> lk(q->mu);
+    nt->ticket = q->next_ticket++;
+    q->notes[nt->ticket] = nt;
+    q->pending.push_back(nt);
+    q->submitted++;
+    q->wait_slot_ms += std::chrono::duration<double, std::milli>(t1 - t0).count();
+    q->copy_ms += std::chrono::duration<double, std::milli>(t2 - t1).count();
+    *ticket = nt->ticket;
+  }
+  q->cv_work.notify_one();
+  return CAPGPU_OK;
+}
+
+extern "C" int capgpu_poll(capgpu_queue* q, uint64_t ticket, int* done) {
+  if (!q || !done) return CAPGPU_ERR_ARG;
+  std::lock_guard<std::mutex> lk(q->mu);
+  auto it = q->notes.find(ticket);
+  if (it == q->notes.end()) return CAPGPU_ERR_ARG;
+  *done = it->second->state == 2;
+  return CAPGPU_OK;
+}
+
+extern "C" int capgpu_wait(capgpu_queue* q, uint64_t ticket, capgpu_proof* out) {
+  if (!q || !out) return CAPGPU_ERR_ARG;
+  std::unique_lock<std::mutex> lk(q->mu);
+  auto it = q->notes.find(ticket);
+  if (it == q->notes.end()) return CAPGPU_ERR_ARG;
+  capgpu_queue::Note* nt = it->second;
+  q->cv_done.wait(lk, [&] { return nt->state == 2; });
+  *out = nt->proof;
+  int status = nt->status;
+  q->notes.erase(it);
+  delete nt;
+  return status;
+}
+
+extern "C" int capgpu_queue_stats(capgpu_queue* q, uint64_t* submitted, uint64_t* completed, uint64_t* groups, double* copy_ms,
+                                  double* wait_slot_ms) {
+  if (!q) return CAPGPU_ERR_ARG;
+  std::lock_guard<std::mutex> lk(q->mu);
+  if (submitted) *submitted = q->submitted;
+  if (completed) *completed = q->completed;
+  if (groups) *groups = q->groups;
+  if (copy_ms) *copy_ms = q->copy_ms;
+  if (wait_slot_ms) *wait_slot_ms = q->wait_slot_ms;
+  return CAPGPU_OK;
+}
+
 extern "C" int capgpu_debug_read(capgpu_ctx* ctx, int what, uint64_t* out, size_t max_elems, size_t* n_elems) {
   if (!ctx || !out || !n_elems) return CAPGPU_ERR_ARG;
   return guarded(ctx, [&] {
     capgpu_job* job = ctx->cached_job;
     CAPGPU_REQUIRE(job != nullptr, "no proof has run on this ctx");
-    const size_t n = job->n, m = job->m, NP = job->NP;
+    const size_t n = job->n, m = job->m, NP = job->NP, G = (size_t)job->G;
     const Fr* src = nullptr;
     size_t rows = 1, len = 0, stride = 0;
+    // proof slot 0 of the last group: row (r, 0) sits at r * G * NP
     switch (what) {
-      case 0: src = job->polys; rows = 5; len = n + 2; stride = NP; break;
+      case 0: src = job->polys; rows = 5; len = n + 2; stride = G * NP; break;
       case 1: src = job->z_eval; len = n; break;
-      case 2: src = job->polys + 6 * NP; len = n + 3; break;
+      case 2: src = job->polys + 6 * G * NP; len = n + 3; break;
       case 3: throw ArgError{"quotient evaluations are overwritten in place by the coset INTT"};
       case 4: src = job->t; len = m; break;
       case 5: src = job->lin; len = n + 3; break;
       case 6: src = job->open; len = n + 3; break;
-      case 7: src = job->shifted; len = n + 3; break;
-      case 8: src = job->polys + 5 * NP; len = n; break;
-      case 9: src = job->split; rows = 5; len = n + 3; stride = NP; break;
+      case 7: src = job->open + G * NP; len = n + 3; break;
+      case 8: src = job->polys + 5 * G * NP; len = n; break;
+      case 9: src = job->split; rows = 5; len = n + 3; stride = G * NP; break;
       default: throw ArgError{"unknown debug item"};
     }
     CAPGPU_REQUIRE(rows * len <= max_elems, "debug buffer too small");

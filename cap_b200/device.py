@@ -48,6 +48,13 @@ class Context:
         except Exception:
             pass
 
+    def set_group(self, group: int):
+        """Notes proved in lockstep by this context inside capgpu_prove_batch / a ProvingQueue."""
+        _lib.check(self.lib.capgpu_ctx_set_group(self.h, group), self.h)
+
+    def set_latency_mode(self, on: bool):
+        _lib.check(self.lib.capgpu_ctx_set_latency_mode(self.h, int(on)), self.h)
+
     def sync(self):
         _lib.check(self.lib.capgpu_ctx_sync(self.h), self.h)
 

@@ -187,7 +187,66 @@ class PlonkKzgSnark:
         return proof_to_dict(PlonkKzgSnark.prove_raw(ctx, pk, wires, pub, bl, extra_transcript_init_msg))
 
 
-def prove_batch_raw(ctxs, pk: ProvingKey, wire_ptrs, pubs, blinders, ext_msgs=None):
+class ProvingQueue:
+    """``capgpu_queue``: asynchronous proving (submit / poll / wait) over the contexts of one GPU.
+    The host-side overlap point is /root/reference/src/proof/transfer.rs:167-181: a caller builds
+    the witness of note k+1 while note k is being proved."""
+
+    def __init__(self, ctxs, pk: ProvingKey, ring_slots: int = 0):
+        self.lib = ctxs[0].lib
+        self.ctxs, self.pk = list(ctxs), pk
+        cx = (c_void_p * len(ctxs))(*[c.h for c in ctxs])
+        h = c_void_p()
+        _lib.check(self.lib.capgpu_queue_create(cx, len(ctxs), pk.h, ring_slots, byref(h)), ctxs[0].h)
+        self.h = h
+
+    def submit(self, wires: np.ndarray, pub_inputs: np.ndarray, blinders: np.ndarray, ext_msg: bytes = b"") -> int:
+        """Copies the inputs (they may be dropped on return) and returns a ticket."""
+        t = ctypes.c_uint64()
+        mbuf = (ctypes.c_uint8 * len(ext_msg)).from_buffer_copy(ext_msg) if ext_msg else None
+        _lib.check(self.lib.capgpu_submit(self.h, _ptr(wires), _ptr(pub_inputs) if pub_inputs.size else None, _ptr(blinders), mbuf,
+                                          len(ext_msg), byref(t)))
+        return t.value
+
+    def submit_ptr(self, wires_ptr: int, pub_inputs: np.ndarray, blinders: np.ndarray, ext_msg: bytes = b"") -> int:
+        t = ctypes.c_uint64()
+        mbuf = (ctypes.c_uint8 * len(ext_msg)).from_buffer_copy(ext_msg) if ext_msg else None
+        _lib.check(self.lib.capgpu_submit(self.h, c_void_p(wires_ptr), _ptr(pub_inputs) if pub_inputs.size else None, _ptr(blinders), mbuf,
+                                          len(ext_msg), byref(t)))
+        return t.value
+
+    def poll(self, ticket: int) -> bool:
+        d = ctypes.c_int()
+        _lib.check(self.lib.capgpu_poll(self.h, ticket, byref(d)))
+        return bool(d.value)
+
+    def wait(self, ticket: int) -> _lib.Proof:
+        """Blocks until the proof is ready; raises PlonkError with the note's status otherwise."""
+        p = _lib.Proof()
+        rc = self.lib.capgpu_wait(self.h, ticket, byref(p))
+        if rc != 0:
+            raise PlonkError(f"capgpu_wait: {self.lib.capgpu_strerror(rc).decode()} ({rc})")
+        return p
+
+    def stats(self) -> dict:
+        a, b, g = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_uint64()
+        c, w = ctypes.c_double(), ctypes.c_double()
+        _lib.check(self.lib.capgpu_queue_stats(self.h, byref(a), byref(b), byref(g), byref(c), byref(w)))
+        return {"submitted": a.value, "completed": b.value, "groups": g.value, "copy_ms": c.value, "wait_slot_ms": w.value}
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.capgpu_queue_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def prove_batch_raw(ctxs, pk: ProvingKey, wire_ptrs, pubs, blinders, ext_msgs=None, on_device: bool = False, raise_on_error: bool = True):
     """``capgpu_prove_batch``: independent notes over one proving key, one worker thread per
     context inside the library (the reference's rayon loop over notes,
     /root/reference/src/utils/params_builder.rs:195-233).  ``wire_ptrs``: host addresses (ints) of
@@ -207,8 +266,9 @@ def prove_batch_raw(ctxs, pk: ProvingKey, wire_ptrs, pubs, blinders, ext_msgs=No
         ml = (c_size_t * count)(*[len(m) if m else 0 for m in ext_msgs])
     else:
         bufs, mp, ml = None, None, None
-    rc = lib.capgpu_prove_batch(cx, len(ctxs), pk.h, count, wp, pp, bp, mp, ml, proofs, status)
-    if rc != 0:
+    fn = lib.capgpu_prove_batch_dev if on_device else lib.capgpu_prove_batch
+    rc = fn(cx, len(ctxs), pk.h, count, wp, pp, bp, mp, ml, proofs, status)
+    if rc != 0 and raise_on_error:
         raise PlonkError(f"capgpu_prove_batch: {lib.capgpu_strerror(rc).decode()} (first failing status {rc})")
     return list(proofs), list(status)
 

@@ -59,6 +59,11 @@ int capgpu_ctx_sync(capgpu_ctx* ctx);
  * bucket reduction (best single-proof latency).  Results are identical either way.  The
  * standalone capgpu_msm_g1 / capgpu_msm_g1_dev calls always use the low-latency schedule. */
 int capgpu_ctx_set_latency_mode(capgpu_ctx* ctx, int on);
+/* Number of notes a context proves in LOCKSTEP when it is handed a batch (capgpu_prove_batch, the
+ * proving queue): every round is issued once for the whole group, so the round's NTT / MSM launches
+ * carry 5-7 vectors per note and one host thread drives `group` proofs.  1 <= group <= 64, default 8
+ * (CAPGPU_GROUP in the environment overrides the default).  Workspace: ~150 MB per note at n = 2^15. */
+int capgpu_ctx_set_group(capgpu_ctx* ctx, int group);
 /* Raw cudaStream_t of the ctx (for callers that time with CUDA events). */
 void* capgpu_ctx_stream(capgpu_ctx* ctx);
 
@@ -139,6 +144,9 @@ int capgpu_preprocess(capgpu_ctx* ctx, const capgpu_srs* srs, unsigned log_n, si
 int capgpu_pk_export(capgpu_ctx* ctx, const capgpu_pk* pk, uint64_t* selectors, uint64_t* sigmas,
                      uint64_t* selector_comms_xy, uint64_t* sigma_comms_xy);
 void capgpu_pk_destroy(capgpu_pk* pk);
+/* Shape of a key: log2 of the domain size, number of public inputs, the 5 coset representatives k
+ * (5 x 4 uint64_t, Montgomery).  Any output pointer may be NULL. */
+int capgpu_pk_info(const capgpu_pk* pk, unsigned* log_n, size_t* num_inputs, uint64_t* k);
 /* Evaluation-form ("Lagrange basis") wire commitments.  Building a proving key also
  * derives, once, the Lagrange commit key L_j = L_j(tau)·G (inverse DFT of the first n SRS points in
  * the group); round 1 then commits the five wire columns straight from their evaluations
@@ -181,15 +189,46 @@ int capgpu_prove(capgpu_ctx* ctx, const capgpu_pk* pk, const uint64_t* wires, co
 int capgpu_prove_dev(capgpu_ctx* ctx, const capgpu_pk* pk, const void* d_wires, const uint64_t* pub_inputs,
                      const uint64_t* blinders, const uint8_t* ext_msg, size_t ext_msg_len, capgpu_proof* out);
 
-/* `count` independent notes over one proving key, spread over `n_ctxs` contexts (one worker thread
- * each, any mix of GPUs as long as `pk` lives on each context's device -- normally 8 contexts of
- * one GPU).  The counterpart of the reference's rayon loop over notes
- * (/root/reference/src/utils/params_builder.rs:195-233).  wires / pub_inputs / blinders / ext_msgs are
- * arrays of `count` pointers; status (optional) receives the per-note code; the return value is the
- * first non-zero code, or 0. */
+/* `count` independent notes over one proving key, spread over `n_ctxs` contexts.  A `capgpu_pk` is
+ * bound to ONE device: every context must live on the key's device (CAPGPU_ERR_ARG otherwise); a
+ * multi-GPU host uploads the key once per GPU and makes one call (or one queue) per GPU.  One worker
+ * thread per context takes groups of up to `group` notes (capgpu_ctx_set_group) and proves each group
+ * in lockstep: 2-4 contexts per GPU saturate a B200.  The counterpart of the reference's rayon loop
+ * over notes (/root/reference/src/utils/params_builder.rs:195-233).  wires / pub_inputs / blinders /
+ * ext_msgs are arrays of `count` pointers (host memory, pageable or pinned); status (optional)
+ * receives the per-note code -- a note whose witness does not satisfy the circuit gets
+ * CAPGPU_ERR_DEGREE without disturbing the other notes of its group; the return value is the first
+ * non-zero code, or 0. */
 int capgpu_prove_batch(capgpu_ctx* const* ctxs, size_t n_ctxs, const capgpu_pk* pk, size_t count,
                        const uint64_t* const* wires, const uint64_t* const* pub_inputs, const uint64_t* const* blinders,
                        const uint8_t* const* ext_msgs, const size_t* ext_msg_lens, capgpu_proof* out, int* status);
+/* Same with every note's 5 x n wire values already resident in device memory of the contexts' GPU. */
+int capgpu_prove_batch_dev(capgpu_ctx* const* ctxs, size_t n_ctxs, const capgpu_pk* pk, size_t count,
+                           const void* const* d_wires, const uint64_t* const* pub_inputs, const uint64_t* const* blinders,
+                           const uint8_t* const* ext_msgs, const size_t* ext_msg_lens, capgpu_proof* out, int* status);
+
+/* ---- asynchronous proving queue ---------------------------------------------------
+ * Lets the host overlap witness generation of note k+1 (`TransferCircuit::build` +
+ * `check_circuit_satisfiability`, /root/reference/src/proof/transfer.rs:167-177) with proving of note
+ * k (:181).  capgpu_submit copies the note's 5 x n wire values from the caller's (pageable) buffer
+ * into a slot of a pinned staging ring and returns a ticket at once -- every input buffer may be
+ * dropped or reused as soon as it returns; it blocks only while the ring is full (back-pressure).
+ * One worker thread per context collects up to `group` pending notes and proves them in lockstep.
+ * capgpu_poll: *done = 1 once the proof is ready.  capgpu_wait: blocks, copies the proof, releases
+ * the ticket and returns the note's status (0, CAPGPU_ERR_DEGREE, ...).  A ticket is waited on once.
+ * ring_slots = 0 lets the library choose (2 x group per context).  All contexts must live on the
+ * key's device.  submit / poll / wait may be called from any thread. */
+typedef struct capgpu_queue capgpu_queue;
+int capgpu_queue_create(capgpu_ctx* const* ctxs, size_t n_ctxs, const capgpu_pk* pk, size_t ring_slots, capgpu_queue** out);
+void capgpu_queue_destroy(capgpu_queue* q);
+int capgpu_submit(capgpu_queue* q, const uint64_t* wires, const uint64_t* pub_inputs, const uint64_t* blinders,
+                  const uint8_t* ext_msg, size_t ext_msg_len, uint64_t* ticket);
+int capgpu_poll(capgpu_queue* q, uint64_t ticket, int* done);
+int capgpu_wait(capgpu_queue* q, uint64_t ticket, capgpu_proof* out);
+/* Counters since creation: notes submitted / completed, lockstep groups formed, host milliseconds
+ * spent copying wire values into the ring and waiting for a free slot (all submitting threads). */
+int capgpu_queue_stats(capgpu_queue* q, uint64_t* submitted, uint64_t* completed, uint64_t* groups, double* copy_ms,
+                       double* wait_slot_ms);
 
 /* ---- round-level API ---------------------------------------------------------------------------
  * For a host that keeps its own transcript (the Rust shim calling upstream's
@@ -200,10 +239,14 @@ int capgpu_job_round2(capgpu_job* job, const uint64_t* beta, const uint64_t* gam
 int capgpu_job_round3(capgpu_job* job, const uint64_t* alpha, const uint64_t* blinders4, uint64_t* split_comms_xy /*5x8*/);
 int capgpu_job_round4(capgpu_job* job, const uint64_t* zeta, uint64_t* evals /*10x4: 5 wires, 4 sigmas, z(zeta*omega)*/);
 int capgpu_job_round5(capgpu_job* job, const uint64_t* v, uint64_t* opening_comms_xy /*2x8*/);
+/* Releases the job's context for the next proof.  A round that FAILS (CUDA error, CAPGPU_ERR_DEGREE)
+ * releases it too: the context accepts a new capgpu_job_begin / capgpu_prove right away, and the
+ * failed handle only accepts capgpu_job_end.  An out-of-order call (CAPGPU_ERR_STATE) leaves the job
+ * as it was. */
 void capgpu_job_end(capgpu_job* job);
 
 /* ---- introspection for tests / benches ---------------------------------------------------------
- * Copies a device-side intermediate of the last proof of this ctx to the host.
+ * Copies a device-side intermediate of the last proof of this ctx (slot 0 of its last group) to the host.
  * what: 0 wire polys (5 x (n+2)), 1 z evals (n), 2 z poly (n+3), 4 quotient poly (8n),
  *       5 linearisation poly (n+3), 6 opening poly (n+3), 7 shifted opening poly (n+3),
  *       8 public-input poly (n), 9 split quotient polys (5 x (n+3)).  */

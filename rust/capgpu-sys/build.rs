@@ -12,7 +12,7 @@ fn main() {
     let mut cmd = Command::new(nvcc);
     cmd.args(["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "--shared",
               "-Xcompiler", "-fPIC", "-o"]).arg(&lib);
-    for f in ["capi.cu", "ntt.cu", "msm.cu", "poly.cu", "prover.cu"] {
+    for f in ["capi.cu", "ntt.cu", "msm.cu", "poly.cu", "prover.cu", "formats.cu"] {
         cmd.arg(csrc.join(f));
         println!("cargo:rerun-if-changed={}", csrc.join(f).display());
     }
@@ -21,4 +21,5 @@ fn main() {
     println!("cargo:rustc-link-search=native={}", out.display());
     println!("cargo:rustc-link-lib=dylib=capgpu");
     println!("cargo:rustc-link-lib=dylib=cudart");
+    println!("cargo:rustc-link-lib=dylib=dl");
 }

@@ -7,6 +7,7 @@ use std::os::raw::{c_char, c_int, c_uint, c_void};
 #[repr(C)] pub struct capgpu_srs { _p: [u8; 0] }
 #[repr(C)] pub struct capgpu_pk { _p: [u8; 0] }
 #[repr(C)] pub struct capgpu_job { _p: [u8; 0] }
+#[repr(C)] pub struct capgpu_queue { _p: [u8; 0] }
 
 #[repr(C)]
 #[derive(Clone, Copy)]
@@ -66,6 +67,17 @@ extern "C" {
     pub fn capgpu_pk_lagrange_export(ctx: *mut capgpu_ctx, pk: *const capgpu_pk, points_xy: *mut u64, count: usize) -> c_int;
     pub fn capgpu_prove_dev(ctx: *mut capgpu_ctx, pk: *const capgpu_pk, d_wires: *const c_void, pub_inputs: *const u64, blinders: *const u64, ext_msg: *const u8, ext_msg_len: usize, out: *mut capgpu_proof) -> c_int;
     pub fn capgpu_prove_batch(ctxs: *const *mut capgpu_ctx, n_ctxs: usize, pk: *const capgpu_pk, count: usize, wires: *const *const u64, pub_inputs: *const *const u64, blinders: *const *const u64, ext_msgs: *const *const u8, ext_msg_lens: *const usize, out: *mut capgpu_proof, status: *mut c_int) -> c_int;
+
+    // lockstep groups, device-resident batches, the asynchronous proving queue
+    pub fn capgpu_ctx_set_group(ctx: *mut capgpu_ctx, group: c_int) -> c_int;
+    pub fn capgpu_pk_info(pk: *const capgpu_pk, log_n: *mut c_uint, num_inputs: *mut usize, k: *mut u64) -> c_int;
+    pub fn capgpu_prove_batch_dev(ctxs: *const *mut capgpu_ctx, n_ctxs: usize, pk: *const capgpu_pk, count: usize, d_wires: *const *const c_void, pub_inputs: *const *const u64, blinders: *const *const u64, ext_msgs: *const *const u8, ext_msg_lens: *const usize, out: *mut capgpu_proof, status: *mut c_int) -> c_int;
+    pub fn capgpu_queue_create(ctxs: *const *mut capgpu_ctx, n_ctxs: usize, pk: *const capgpu_pk, ring_slots: usize, out: *mut *mut capgpu_queue) -> c_int;
+    pub fn capgpu_queue_destroy(q: *mut capgpu_queue);
+    pub fn capgpu_submit(q: *mut capgpu_queue, wires: *const u64, pub_inputs: *const u64, blinders: *const u64, ext_msg: *const u8, ext_msg_len: usize, ticket: *mut u64) -> c_int;
+    pub fn capgpu_poll(q: *mut capgpu_queue, ticket: u64, done: *mut c_int) -> c_int;
+    pub fn capgpu_wait(q: *mut capgpu_queue, ticket: u64, out: *mut capgpu_proof) -> c_int;
+    pub fn capgpu_queue_stats(q: *mut capgpu_queue, submitted: *mut u64, completed: *mut u64, groups: *mut u64, copy_ms: *mut f64, wait_slot_ms: *mut f64) -> c_int;
 
     // diagnostics
     pub fn capgpu_debug_read(ctx: *mut capgpu_ctx, what: c_int, out: *mut u64, max_elems: usize, n_elems: *mut usize) -> c_int;

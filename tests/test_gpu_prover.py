@@ -266,6 +266,125 @@ def test_prove_batch_matches_single_proofs(ctx):
     srs.close()
 
 
+@pytest.mark.parametrize("group,n_ctxs,count", [(8, 1, 5), (3, 2, 7), (2, 2, 1), (64, 1, 9)])
+def test_lockstep_groups_equal_single_proofs(ctx, group, n_ctxs, count):
+    """A context proving `group` notes in lockstep (one launch per round for the whole group; SURVEY
+    8f N2) returns, note for note, the bytes of the single-note call -- for full, partial and
+    single-note groups, host and device-resident inputs; an unsatisfied witness fails its own slot
+    (CAPGPU_ERR_DEGREE) and nothing else."""
+    import torch
+    from cap_b200 import device
+    circ = synth.make_circuit(8, num_inputs=3, seed=12)
+    srs = plonk.PlonkKzgSnark.universal_setup(ctx, circ.n + 2, TAU)
+    pk = plonk.PlonkKzgSnark.preprocess(ctx, srs, circ)
+    ctxs = [device.Context(0) for _ in range(n_ctxs)]
+    for c in ctxs:
+        c.set_group(group)
+    circs = [circ] + [circ.with_witness(s) for s in range(1, count)]
+    wires = [plonk.wire_values(c) for c in circs]
+    pubs = [field.fr_to_mont_array(plonk.public_input(c)) for c in circs]
+    rng = random.Random(group * 100 + count)
+    bls = [field.fr_raw_array(_mont([rng.randrange(B.R) for _ in range(17)])) for _ in circs]
+    msgs = [b"g-%d" % i if i % 3 else b"" for i in range(count)]
+    singles = [bytes(plonk.PlonkKzgSnark.prove_raw(ctx, pk, wires[i], pubs[i], bls[i], msgs[i])) for i in range(count)]
+    proofs, status = plonk.prove_batch_raw(ctxs, pk, [w.ctypes.data for w in wires], pubs, bls, msgs)
+    assert status == [0] * count
+    assert [bytes(p) for p in proofs] == singles
+    dw = [torch.from_numpy(w.view(np.int64)).cuda() for w in wires]
+    proofs, status = plonk.prove_batch_raw(ctxs, pk, [t.data_ptr() for t in dw], pubs, bls, msgs, on_device=True)
+    assert status == [0] * count and [bytes(p) for p in proofs] == singles
+    if count >= 3:
+        bad = wires[1].copy()
+        bad[4, circ.num_inputs + 1, 0] ^= 1
+        ws = [wires[0], bad] + wires[2:]
+        proofs, status = plonk.prove_batch_raw(ctxs, pk, [w.ctypes.data for w in ws], pubs, bls, msgs, raise_on_error=False)
+        assert status == [0, -3] + [0] * (count - 2)
+        assert [bytes(p) for i, p in enumerate(proofs) if i != 1] == [s for i, s in enumerate(singles) if i != 1]
+    for c in ctxs:
+        c.close()
+    pk.close()
+    srs.close()
+
+
+def test_proving_queue_submit_poll_wait(ctx):
+    """capgpu_submit copies its inputs (the caller's buffers are scribbled over right after the
+    call), tickets complete in any wait order, poll turns true, a bad note reports its own status,
+    and every proof equals the synchronous single-note proof."""
+    import time
+    from cap_b200 import device
+    circ = synth.make_circuit(9, num_inputs=4, seed=5)
+    srs = plonk.PlonkKzgSnark.universal_setup(ctx, circ.n + 2, TAU)
+    pk = plonk.PlonkKzgSnark.preprocess(ctx, srs, circ)
+    count = 11
+    circs = [circ] + [circ.with_witness(s) for s in range(1, count)]
+    wires = [plonk.wire_values(c) for c in circs]
+    pubs = [field.fr_to_mont_array(plonk.public_input(c)) for c in circs]
+    rng = random.Random(77)
+    bls = [field.fr_raw_array(_mont([rng.randrange(B.R) for _ in range(17)])) for _ in circs]
+    msgs = [b"q-%d" % i for i in range(count)]
+    singles = [bytes(plonk.PlonkKzgSnark.prove_raw(ctx, pk, wires[i], pubs[i], bls[i], msgs[i])) for i in range(count)]
+    ctxs = [device.Context(0), device.Context(0)]
+    for c in ctxs:
+        c.set_group(4)
+    q = plonk.ProvingQueue(ctxs, pk, ring_slots=3)  # fewer slots than notes: submit exercises back-pressure
+    tickets = []
+    for i in range(count):
+        w, p, b = wires[i].copy(), pubs[i].copy(), bls[i].copy()
+        if i == 6:
+            w[4, circ.num_inputs + 2, 0] ^= 1  # unsatisfied witness
+        tickets.append(q.submit(w, p, b, msgs[i]))
+        w[:] = 0xDEADBEEF
+        p[:] = 1
+        b[:] = 2
+    deadline = time.time() + 60
+    while not q.poll(tickets[-1]):
+        assert time.time() < deadline
+        time.sleep(0.001)
+    for i in reversed(range(count)):
+        if i == 6:
+            with pytest.raises(plonk.PlonkError, match="degree"):
+                q.wait(tickets[i])
+        else:
+            assert bytes(q.wait(tickets[i])) == singles[i], i
+    st = q.stats()
+    assert st["submitted"] == st["completed"] == count and 1 <= st["groups"] <= count
+    assert ctx.lib.capgpu_poll(q.h, tickets[0], byref(ctypes.c_int())) == -2  # a ticket is consumed by wait
+    q.close()
+    for c in ctxs:
+        c.close()
+    pk.close()
+    srs.close()
+
+
+def test_failed_round_releases_the_context(ctx):
+    """a round that fails (unsatisfied circuit -> CAPGPU_ERR_DEGREE in round 3) must not
+    wedge the context: a fresh capgpu_job_begin succeeds without capgpu_job_end on the failed job."""
+    circ = synth.make_circuit(6, num_inputs=2, seed=8)
+    srs = plonk.PlonkKzgSnark.universal_setup(ctx, circ.n + 2, TAU)
+    pk = plonk.PlonkKzgSnark.preprocess(ctx, srs, circ)
+    lib = ctx.lib
+    wires = plonk.wire_values(circ)
+    bad = wires.copy()
+    bad[4, circ.num_inputs + 1, 0] ^= 1
+    pub = field.fr_to_mont_array(plonk.public_input(circ))
+    bl = field.fr_raw_array(_mont(list(range(5, 22))))
+    one = field.fr_to_mont_array([7])
+    job = c_void_p()
+    _lib.check(lib.capgpu_job_begin(ctx.h, pk.h, _ptr(bad), _ptr(pub), byref(job)), ctx.h)
+    c5 = np.zeros((5, 8), dtype=np.uint64)
+    _lib.check(lib.capgpu_job_round1(job, _ptr(bl[:10].copy()), _ptr(c5)), ctx.h)
+    _lib.check(lib.capgpu_job_round2(job, _ptr(one), _ptr(one), _ptr(bl[10:13].copy()), _ptr(c5)), ctx.h)
+    assert lib.capgpu_job_round3(job, _ptr(one), _ptr(bl[13:].copy()), _ptr(c5)) == -3
+    assert lib.capgpu_job_round4(job, _ptr(one), _ptr(c5)) == -5  # the failed job is closed
+    job2 = c_void_p()
+    _lib.check(lib.capgpu_job_begin(ctx.h, pk.h, _ptr(wires), _ptr(pub), byref(job2)), ctx.h)
+    lib.capgpu_job_end(job2)
+    good = plonk.PlonkKzgSnark.prove_raw(ctx, pk, wires, pub, bl, b"")
+    assert oplonk.verify(pk.vk, plonk.public_input(circ), plonk.proof_to_dict(good), TAU)
+    pk.close()
+    srs.close()
+
+
 @pytest.mark.parametrize("log_n", [3, 6, 9])
 def test_lagrange_commit_key(ctx, log_n):
     """The derived evaluation-form commit key is [L_j(tau) G] followed by P_0, P_1, P_n, P_{n+1}."""
