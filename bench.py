@@ -52,13 +52,15 @@ def parse_args():
     ap.add_argument("--impl", default="capgpu", choices=["capgpu", "reference"])
     ap.add_argument("--workload", default="transfer_2x2")
     ap.add_argument("--batch", type=int, default=64, help="independent notes per GPU per step")
-    ap.add_argument("--ctxs", type=int, default=4, help="prover contexts (host thread + CUDA stream) per GPU")
+    ap.add_argument("--ctxs", type=int, default=int(os.environ.get("BENCH_CTXS", "4")), help="prover contexts (host thread + CUDA stream) per GPU")
     ap.add_argument("--group", type=int, default=8, help="notes a context proves in lockstep (capgpu_ctx_set_group)")
     ap.add_argument("--cpu-sample", type=int, default=-1, help="proofs in the cpu_baseline sample (-1: one per host thread, 0 disables)")
     ap.add_argument("--witness", default="dense", choices=["dense", "sparse"],
                     help="dense: uniform witness (the headline workload); sparse: 45%% of gate inputs unused (zero variable), "
                          "half of the fresh inputs boolean — closer to jf-relation gadget circuits; exercises the evaluation-form commitments")
     ap.add_argument("--no-lagrange", action="store_true", help="commit wire polynomials from coefficients (A/B against the evaluation-form path)")
+    ap.add_argument("--fixture", default=None, help="CAPFIX01 replay fixture (rust/parity-dump): prove ITS key / witness / RNG words instead of the "
+                                                     "synthetic workload and compare the proof bytes with the recorded ones")
     ap.add_argument("--no-extras", action="store_true", help="skip roofline / MSM-latency / cpu_baseline side measurements")
     return ap.parse_args()
 
@@ -139,15 +141,30 @@ def run_capgpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     assert world == args.gpus or world == 1, f"launched with WORLD_SIZE={world} but --gpus {args.gpus}"
 
-    circ, circs, wires, pubs, bl = build_workload(args.workload, args.witness)
-    n = circ.n
     ctxs = [device.Context(local) for _ in range(args.ctxs)]
     for c in ctxs:
         c.set_group(args.group)
     ctx0 = ctxs[0]
     lib = ctx0.lib
-    srs = plonk.PlonkKzgSnark.universal_setup(ctx0, n + 2, TAU)
-    pk = plonk.PlonkKzgSnark.preprocess(ctx0, srs, circ)
+    fixture_info = None
+    if args.fixture:
+        # a recorded reference proof: its serialized ProvingKey (commit key included), witness columns and RNG words
+        from cap_b200 import fixture as fxm
+        fx = fxm.Fixture(args.fixture)
+        hpk = fx.load_key(ctx0)
+        lg, ni = ctypes.c_uint(), ctypes.c_size_t()
+        _lib.check(lib.capgpu_pk_info(hpk, ctypes.byref(lg), ctypes.byref(ni), None))
+        pk = plonk.ProvingKey(ctx0, None, hpk, lg.value, ni.value, ())
+        fbl, draws = fx.blinders(lib)
+        circ = type("FixtureCircuit", (), {"n": 1 << lg.value, "log_n": lg.value, "num_inputs": ni.value})()
+        wires, pubs, bl = [fx.wires] * N_WITNESSES, [fx.pub_inputs] * N_WITNESSES, np.stack([fbl] * N_WITNESSES)
+        srs = None
+        args.no_extras = True
+    else:
+        circ, circs, wires, pubs, bl = build_workload(args.workload, args.witness)
+        srs = plonk.PlonkKzgSnark.universal_setup(ctx0, circ.n + 2, TAU)
+        pk = plonk.PlonkKzgSnark.preprocess(ctx0, srs, circ)
+    n = circ.n
     if args.no_lagrange:
         pk.set_lagrange(False)
 
@@ -156,8 +173,8 @@ def run_capgpu(args):
     wires_dev = [torch.from_numpy(w.view(np.int64)).cuda() for w in wires]
     torch.cuda.synchronize()
     wires_host = [wires[i % N_WITNESSES].copy() for i in range(args.batch)]
-    ext = b"bench-ext-msg"
-    ext_buf = (ctypes.c_uint8 * len(ext)).from_buffer_copy(ext)
+    ext = fx.ext_msg if args.fixture else b"bench-ext-msg"
+    ext_buf = (ctypes.c_uint8 * len(ext)).from_buffer_copy(ext) if ext else None
     from ctypes import byref, c_void_p
 
     def prove_one(ci: int, i: int, on_device: bool, out: _lib.Proof):
@@ -226,6 +243,12 @@ def run_capgpu(args):
     k = args.group + 1
     grp, st = plonk.prove_batch_raw(ctxs, pk, batch_dptrs[:k], batch_pubs[:k], batch_bl[:k], batch_msgs[:k], on_device=True)
     assert bytes(grp[1]) == bytes(pa) and not any(st), "lockstep group proof differs from the single proof"
+    if args.fixture:
+        got = fxm.proof_bytes(lib, grp[0])
+        fixture_info = {"file": os.path.basename(args.fixture), "note_meta": list(fx.meta), "rng_draws": draws,
+                        "proof_bytes_match": got == fx.proof_bytes}
+        if not fixture_info["proof_bytes_match"]:
+            sys.stderr.write("bench.py --fixture: GPU proof bytes DIFFER from the recorded proof\n")
 
     ms_dev, clocks, launches, _ = timed(steps_dev, True)
     qs0 = queue.stats()
@@ -259,6 +282,11 @@ def run_capgpu(args):
         "gpu_launches": launches,
     }
     queue.close()
+    if world > 1 and not args.no_extras and not args.fixture:
+        line["msm_2p17_split"] = split_msm_measurement(torch, dist, ctx0, world)  # collective: every rank takes part
+    if fixture_info:
+        line["fixture"] = fixture_info
+        line["config"]["workload"] = f"fixture {fixture_info['file']}: TurboPlonk prove, domain n=2^{circ.log_n}, {circ.num_inputs} public inputs, BN254"
 
     if rank == 0 and not args.no_extras:
         def prove_group0():
@@ -270,6 +298,48 @@ def run_capgpu(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def split_msm_measurement(torch, dist, ctx, world):
+    """ONE 2^17-point MSM split by bucket range over the ranks (cap_b200.shard.SplitMsm: slice kernels,
+    NCCL all-gather of the 64-byte slice results over NVLink and the EC fold, all on the context
+    stream), beside the same MSM on one GPU.  CUDA events, max over ranks, median of 10."""
+    from ctypes import c_void_p
+    from cap_b200 import _lib, device, field, shard
+    n17 = 1 << 17
+    srs17 = device.Srs(ctx, tau_mont=field.fr_to_mont_array([TAU % field.R])[0], size=n17)
+    g = torch.Generator(device="cuda").manual_seed(1)  # same scalars on every rank
+    sc = torch.randint(-(1 << 63), (1 << 63) - 1, (n17, 4), dtype=torch.int64, device="cuda", generator=g)
+    sc[:, 3] &= (1 << 60) - 1
+    split = shard.SplitMsm(ctx, srs17)
+    stream = torch.cuda.ExternalStream(ctx.stream)
+    out1 = torch.zeros(8, dtype=torch.int64, device="cuda")
+
+    def timed(fn):
+        ts = []
+        for _ in range(12):
+            dist.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            e1.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ts.append(float(t.item()))
+        return statistics.median(ts[2:])
+
+    res = split(sc)
+    ctx.sync()
+    _lib.check(ctx.lib.capgpu_msm_g1_dev(ctx.h, srs17.h, 0, c_void_p(sc.data_ptr()), n17, 1, 0, c_void_p(out1.data_ptr())), ctx.h)
+    ctx.sync()
+    same = bool(torch.equal(res, out1))
+    split_ms = timed(lambda: split(sc))
+    single_ms = timed(lambda: _lib.check(ctx.lib.capgpu_msm_g1_dev(ctx.h, srs17.h, 0, c_void_p(sc.data_ptr()), n17, 1, 0, c_void_p(out1.data_ptr())), ctx.h))
+    srs17.close()
+    return {"points": n17, "n_gpus": world, "split": "bucket range, slice results all-gathered over NCCL/NVLink on the context stream",
+            "ms": split_ms, "single_gpu_ms": single_ms, "speedup": single_ms / split_ms, "equals_single_gpu_result": same}
 
 
 def side_measurements(args, torch, ctxs, pk, srs, circ, wires_dev, wires, pubs, bl, prove_one, world, prove_group0):

@@ -21,6 +21,7 @@ EXPORTS = [
     "capgpu_job_round4", "capgpu_job_round5", "capgpu_job_end", "capgpu_debug_read", "capgpu_launch_count",
     "capgpu_calibrate", "capgpu_prove_dev", "capgpu_profile_enable", "capgpu_profile_read", "capgpu_ctx_set_latency_mode", "capgpu_g1_sum_dev", "capgpu_srs_upload_compressed", "capgpu_prove_batch",
     "capgpu_ctx_set_group", "capgpu_pk_info", "capgpu_prove_batch_dev", "capgpu_queue_create", "capgpu_queue_destroy", "capgpu_submit", "capgpu_poll", "capgpu_wait", "capgpu_queue_stats",
+    "capgpu_sha256", "capgpu_srs_load_serialized", "capgpu_pk_load_serialized", "capgpu_proof_serialize", "capgpu_fr_rand_from_words", "capgpu_msm_g1_dev_part",
 ]
 
 
@@ -75,6 +76,7 @@ def load() -> ctypes.CDLL:
         "capgpu_srs_export": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t]),
         "capgpu_msm_g1_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, c_int, c_void_p]),
         "capgpu_ntt_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_uint, c_size_t, c_int, c_int]),
+        "capgpu_msm_g1_dev_part": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_int, c_size_t, c_size_t, c_void_p]),
         "capgpu_g1_sum_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
         "capgpu_srs_destroy": (None, [c_void_p]),
         "capgpu_srs_size": (c_size_t, [c_void_p]),
@@ -100,6 +102,11 @@ def load() -> ctypes.CDLL:
         "capgpu_submit": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, POINTER(c_uint64)]),
         "capgpu_poll": (c_int, [c_void_p, c_uint64, POINTER(c_int)]),
         "capgpu_wait": (c_int, [c_void_p, c_uint64, POINTER(Proof)]),
+        "capgpu_sha256": (c_int, [c_void_p, c_size_t, c_void_p]),
+        "capgpu_srs_load_serialized": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_int, POINTER(c_void_p)]),
+        "capgpu_pk_load_serialized": (c_int, [c_void_p, c_void_p, c_size_t, POINTER(c_size_t), POINTER(c_void_p)]),
+        "capgpu_proof_serialize": (c_int, [POINTER(Proof), c_void_p, c_size_t, POINTER(c_size_t)]),
+        "capgpu_fr_rand_from_words": (c_int, [c_void_p, c_size_t, c_void_p, c_size_t, POINTER(c_size_t)]),
         "capgpu_queue_stats": (c_int, [c_void_p, POINTER(c_uint64), POINTER(c_uint64), POINTER(c_uint64), POINTER(c_double), POINTER(c_double)]),
         "capgpu_job_begin": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_void_p)]),
         "capgpu_job_round1": (c_int, [c_void_p, c_void_p, c_void_p]),

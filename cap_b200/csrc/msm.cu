@@ -26,6 +26,7 @@
 #include "common.cuh"
 #include <stdlib.h>
 #include <string.h>
+#include <vector>
 
 namespace capgpu {
 
@@ -107,7 +108,9 @@ __global__ void msm_decompress(const uint32_t* __restrict__ bytes, G1Affine* tab
 // recode + histogram
 // ------------------------------------------------------------------------------------------
 __global__ void msm_recode(const Fr* scalars, size_t n, size_t stride, int mont, int c, int W, int32_t* digits,
-                           uint32_t* counts, size_t K) {
+                           uint32_t* counts, size_t K, uint32_t lo) {
+  // K buckets are handled by this launch: magnitudes lo + 1 .. lo + K (a bucket-range slice of a
+  // split MSM; lo = 0 and K = 2^(c-1) otherwise); digits outside the slice are dropped here
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const size_t b = blockIdx.y;
@@ -129,8 +132,10 @@ __global__ void msm_recode(const Fr* scalars, size_t n, size_t stride, int mont,
     int32_t d = (int32_t)v + carry;
     carry = 0;
     if (d > half) { d -= (1 << c); carry = 1; }
+    uint32_t mag = (uint32_t)(d < 0 ? -d : d);
+    if (mag <= lo || mag > lo + K) d = 0;
     digits[(b * W + w) * n + i] = d;
-    if (d != 0) atomicAdd(&cnt[d < 0 ? -d : d], 1u);
+    if (d != 0) atomicAdd(&cnt[mag - lo], 1u);
   }
 }
 
@@ -203,13 +208,13 @@ __global__ void msm_scan(uint32_t* counts, uint32_t* cursors, uint32_t* order, s
 }
 
 __global__ void msm_scatter(const int32_t* digits, size_t n, int W, uint32_t* cursors, uint32_t* entries, size_t K,
-                            size_t table_n, size_t base_off) {
+                            size_t table_n, size_t base_off, uint32_t lo) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const size_t w = blockIdx.y, b = blockIdx.z;
   int32_t d = digits[(b * W + w) * n + i];
   if (d == 0) return;
-  uint32_t k = d < 0 ? (uint32_t)(-d) : (uint32_t)d;
+  uint32_t k = (d < 0 ? (uint32_t)(-d) : (uint32_t)d) - lo;
   uint32_t pos = atomicAdd(&cursors[b * (K + 2) + k], 1u);
   uint32_t idx = (uint32_t)(w * table_n + base_off + i);
   entries[b * ((size_t)W * n) + pos] = idx | (d < 0 ? 0x80000000u : 0u);
@@ -402,7 +407,7 @@ __device__ inline G1XYZZ block_reduce_xyzz(G1XYZZ v, G1XYZZ* smem /* >= 32 entri
 }
 
 __global__ void __launch_bounds__(128) msm_reduce_segments(const G1XYZZ* __restrict__ buckets, size_t K, uint32_t L,
-                                                           G1XYZZ* partials) {
+                                                           G1XYZZ* partials, uint32_t wbase) {
   __shared__ G1XYZZ smem[32];
   const size_t T = K / L;
   const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -416,7 +421,7 @@ __global__ void __launch_bounds__(128) msm_reduce_segments(const G1XYZZ* __restr
       xyzz_add(running, q);
       xyzz_add(acc, running);
     }
-    v = xyzz_mul_small(running, (uint32_t)(t * L));
+    v = xyzz_mul_small(running, (uint32_t)(t * L) + wbase);  // bucket j of this slice weighs wbase + j + 1
     xyzz_add(v, acc);
   }
   v = block_reduce_xyzz(v, smem);
@@ -526,7 +531,7 @@ __device__ inline G1XYZZ block_reduce_xyzz_pair(G1XYZZ v, G1XYZZ* smem /* >= 32 
 
 // msm_reduce_segments with one lane PAIR per segment
 __global__ void __launch_bounds__(256) msm_reduce_segments_pair(const G1XYZZ* __restrict__ buckets, size_t K, uint32_t L,
-                                                                G1XYZZ* partials) {
+                                                                G1XYZZ* partials, uint32_t wbase) {
   __shared__ G1XYZZ smem[32];
   const size_t T = K / L;
   const size_t t = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
@@ -542,7 +547,7 @@ __global__ void __launch_bounds__(256) msm_reduce_segments_pair(const G1XYZZ* __
       xyzz_add_pair(running, q, role, pmask);
       xyzz_add_pair(acc, running, role, pmask);
     }
-    v = xyzz_mul_small_pair(running, (uint32_t)(t * L), role, pmask);
+    v = xyzz_mul_small_pair(running, (uint32_t)(t * L) + wbase, role, pmask);
     xyzz_add_pair(v, acc, role, pmask);
   }
   v = block_reduce_xyzz_pair(v, smem, role, pmask);
@@ -584,6 +589,21 @@ __global__ void msm_finalize(const G1XYZZ* partials, uint32_t nparts, G1Affine* 
 // ------------------------------------------------------------------------------------------
 static int ceil_log2(size_t x) { int l = 0; while (((size_t)1 << l) < x) l++; return l; }
 
+// Window size c (2^(c-1) buckets, W = ceil(255 / c) window-shifted tables).  Bucket accumulation costs
+// n W mixed additions, the bucket reduction ~2.8 full additions per bucket at half the lane efficiency.
+// Measured on one lockstep group of 8 proofs at n = 2^15 (profiles/r2_launches_group8.csv): with c = 16
+// the reduction took 0.53 of the accumulation time; c = floor(log2 n) balances the two (c = 15 at
+// n = 2^15: 6 % more additions, half the buckets).  A lone MSM of 2^12..2^14 points is latency-bound
+// (bucket chains, then the reduction) and prefers many short buckets: c >= 15 there.
+static int choose_window(size_t n_points) {
+  int c = ceil_log2(n_points + 1) - 1;  // floor(log2 n)
+  if (c > 16) c = 16;
+  if (c < 4) c = 4;
+  if (n_points >= ((size_t)1 << 12) && c < 15) c = 15;
+  if (const char* e = getenv("CAPGPU_WINDOW_BITS")) { int v = atoi(e); if (v >= 2 && v <= 16) c = v; }  // A/B runs only
+  return c;
+}
+
 struct MsmTuning {
   int red_seg;         // buckets per thread in the segmented reduction (0 = heuristic)
   size_t acc_threads;  // target thread count when choosing lanes per bucket
@@ -606,27 +626,30 @@ static const MsmTuning& msm_tuning() {
 }
 
 template <int LPB, int MINB>
-static void launch_accumulate2(capgpu_ctx* ctx, const capgpu_srs* srs, const uint32_t* entries, const uint32_t* offsets,
+static void launch_accumulate2(capgpu_ctx* ctx, const capgpu_srs* srs, size_t K, const uint32_t* entries, const uint32_t* offsets,
                                const uint32_t* order, G1XYZZ* buckets, size_t entries_stride, size_t batch, uint32_t heavy_thr) {
-  size_t threads = srs->K * LPB;
+  size_t threads = K * LPB;
   const unsigned block = msm_tuning().acc_block;
   dim3 grid((unsigned)batch, ceil_div(threads, (size_t)block));
-  msm_accumulate<LPB, MINB><<<grid, block, 0, ctx->stream>>>(srs->table, entries, offsets, order, buckets, srs->K, entries_stride, heavy_thr);
+  msm_accumulate<LPB, MINB><<<grid, block, 0, ctx->stream>>>(srs->table, entries, offsets, order, buckets, K, entries_stride, heavy_thr);
   CAPGPU_LAUNCH_CHECK(ctx);
 }
 
 template <int LPB>
-static void launch_accumulate(capgpu_ctx* ctx, const capgpu_srs* srs, const uint32_t* entries, const uint32_t* offsets,
+static void launch_accumulate(capgpu_ctx* ctx, const capgpu_srs* srs, size_t K, const uint32_t* entries, const uint32_t* offsets,
                               const uint32_t* order, G1XYZZ* buckets, size_t entries_stride, size_t batch, uint32_t heavy_thr) {
-  launch_accumulate2<LPB, 4>(ctx, srs, entries, offsets, order, buckets, entries_stride, batch, heavy_thr);
+  launch_accumulate2<LPB, 4>(ctx, srs, K, entries, offsets, order, buckets, entries_stride, batch, heavy_thr);
 }
 
 void msm_device(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const Fr* scalars, size_t n, size_t stride,
-                size_t batch, bool scalars_mont, G1Affine* out_dev, bool latency) {
+                size_t batch, bool scalars_mont, G1Affine* out_dev, bool latency, size_t part, size_t parts) {
   if (batch == 0) return;
   if (base_off + n > srs->n) throw CodeError{CAPGPU_ERR_SRS_TOO_SMALL};
   CAPGPU_REQUIRE(srs->device == ctx->device, "SRS lives on another device");
-  const size_t K = srs->K;
+  CAPGPU_REQUIRE(parts >= 1 && part < parts && srs->K % parts == 0, "bucket-range split must divide the bucket count");
+  // bucket-range slice `part` of `parts` (split MSM across GPUs): this launch owns magnitudes lo+1 .. lo+K
+  const size_t K = srs->K / parts;
+  const uint32_t lo = (uint32_t)(part * K);
   const int W = srs->W, c = srs->c;
   if (n == 0) {
     CAPGPU_CUDA(cudaMemsetAsync(out_dev, 0, batch * sizeof(G1Affine), ctx->stream));
@@ -648,32 +671,44 @@ void msm_device(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const F
   CAPGPU_CUDA(cudaMemsetAsync(counts, 0, batch * (K + 2) * sizeof(uint32_t), ctx->stream));
   {
     dim3 grid(ceil_div(n, 128), (unsigned)batch);
-    msm_recode<<<grid, 128, 0, ctx->stream>>>(scalars, n, stride, scalars_mont ? 1 : 0, c, W, digits, counts, K);
+    msm_recode<<<grid, 128, 0, ctx->stream>>>(scalars, n, stride, scalars_mont ? 1 : 0, c, W, digits, counts, K, lo);
     CAPGPU_LAUNCH_CHECK(ctx);
   }
   msm_scan<<<(unsigned)batch, 1024, 0, ctx->stream>>>(counts, cursors, order, K);
   CAPGPU_LAUNCH_CHECK(ctx);
   {
     dim3 grid(ceil_div(n, 256), (unsigned)W, (unsigned)batch);
-    msm_scatter<<<grid, 256, 0, ctx->stream>>>(digits, n, W, cursors, entries, K, srs->n, base_off);
+    msm_scatter<<<grid, 256, 0, ctx->stream>>>(digits, n, W, cursors, entries, K, srs->n, base_off, lo);
     CAPGPU_LAUNCH_CHECK(ctx);
   }
   }
   // lanes per bucket: aim for ~128k accumulating threads
   size_t lpb = 1;
   // ... but never so many that a lane gets fewer than ~8 additions (the lane tree costs log2(lpb) full adds)
-  const size_t avg_entries = (size_t)W * n / K;
+  const size_t avg_entries = (size_t)W * n / srs->K;
   while (lpb < 32 && batch * K * lpb * 2 <= msm_tuning().acc_threads && lpb * 2 * 8 <= avg_entries) lpb <<= 1;
   const size_t es = (size_t)W * n;
   const uint32_t heavy_thr = (uint32_t)(8 * avg_entries > MSM_HEAVY ? 8 * avg_entries : MSM_HEAVY);
   // one-wave launches in the low-latency schedule: equal chunks of sorted entries per thread
   const size_t wave_threads = (size_t)ctx->sm_count * 4 * 128;
-  const bool flat = latency && msm_tuning().flat && batch * K * lpb <= wave_threads && es >= 4 * wave_threads;
+  // mixed additions of this call = non-zero digits kept by the recode (read back only while profiling:
+  // zero witness cells and bucket-range slices make the digit-slot count batch * W * n an overestimate)
+  double additions = (double)batch * W * n / parts;
+  if (ctx->profile) {
+    std::vector<uint32_t> totals(batch);
+    CAPGPU_CUDA(cudaMemcpy2DAsync(totals.data(), sizeof(uint32_t), counts + K + 1, (K + 2) * sizeof(uint32_t), sizeof(uint32_t), batch,
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+    CAPGPU_CUDA(cudaStreamSynchronize(ctx->stream));
+    additions = 0;
+    for (uint32_t t : totals) additions += t;
+  }
+  const size_t ee = es / parts;  // expected entries of this bucket-range slice
+  const bool flat = latency && msm_tuning().flat && batch * K * lpb <= wave_threads && ee >= 4 * wave_threads;
   if (flat) {
-    ProfScope prof_acc(ctx, PROF_MSM_ACCUMULATE, (double)batch * W * n);
+    ProfScope prof_acc(ctx, PROF_MSM_ACCUMULATE, additions);
     const size_t per_vec_threads = wave_threads / batch;
-    const uint32_t S = (uint32_t)((es + per_vec_threads - 1) / per_vec_threads);
-    const size_t nthreads = (es + S - 1) / S;
+    const uint32_t S = (uint32_t)((ee + per_vec_threads - 1) / per_vec_threads);
+    const size_t nthreads = (es + S - 1) / S;  // covers the worst case (every digit in this slice); idle threads exit at once
     ctx->msm_flat.reserve(2 * batch * nthreads * sizeof(G1XYZZ));
     G1XYZZ* pfirst = ctx->msm_flat.as<G1XYZZ>();
     G1XYZZ* plast = pfirst + batch * nthreads;
@@ -691,15 +726,14 @@ void msm_device(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const F
     msm_accumulate_heavy<<<grid, 128, 0, ctx->stream>>>(srs->table, entries, counts, order, buckets, K, es, heavy_thr);
     CAPGPU_LAUNCH_CHECK(ctx);
   } else {
-  // units: upper bound on mixed additions (one per non-zero digit; zero digits have probability 2^-c)
-  ProfScope prof_acc(ctx, PROF_MSM_ACCUMULATE, (double)batch * W * n);
+  ProfScope prof_acc(ctx, PROF_MSM_ACCUMULATE, additions);
   switch (lpb) {
-    case 1: launch_accumulate<1>(ctx, srs, entries, counts, order, buckets, es, batch, heavy_thr); break;
-    case 2: launch_accumulate<2>(ctx, srs, entries, counts, order, buckets, es, batch, heavy_thr); break;
-    case 4: launch_accumulate<4>(ctx, srs, entries, counts, order, buckets, es, batch, heavy_thr); break;
-    case 8: launch_accumulate<8>(ctx, srs, entries, counts, order, buckets, es, batch, heavy_thr); break;
-    case 16: launch_accumulate<16>(ctx, srs, entries, counts, order, buckets, es, batch, heavy_thr); break;
-    default: launch_accumulate<32>(ctx, srs, entries, counts, order, buckets, es, batch, heavy_thr); break;
+    case 1: launch_accumulate<1>(ctx, srs, K, entries, counts, order, buckets, es, batch, heavy_thr); break;
+    case 2: launch_accumulate<2>(ctx, srs, K, entries, counts, order, buckets, es, batch, heavy_thr); break;
+    case 4: launch_accumulate<4>(ctx, srs, K, entries, counts, order, buckets, es, batch, heavy_thr); break;
+    case 8: launch_accumulate<8>(ctx, srs, K, entries, counts, order, buckets, es, batch, heavy_thr); break;
+    case 16: launch_accumulate<16>(ctx, srs, K, entries, counts, order, buckets, es, batch, heavy_thr); break;
+    default: launch_accumulate<32>(ctx, srs, K, entries, counts, order, buckets, es, batch, heavy_thr); break;
   }
   {
     dim3 grid((unsigned)(K < 64 ? K : 64), (unsigned)batch);
@@ -727,8 +761,8 @@ void msm_device(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const F
   const bool pair = latency && msm_tuning().pair;  // lane-pair cooperative group operations
   {
     dim3 grid(nblocks, (unsigned)batch);
-    if (pair) msm_reduce_segments_pair<<<grid, 2 * block, 0, ctx->stream>>>(buckets, K, L, partials);
-    else msm_reduce_segments<<<grid, block, 0, ctx->stream>>>(buckets, K, L, partials);
+    if (pair) msm_reduce_segments_pair<<<grid, 2 * block, 0, ctx->stream>>>(buckets, K, L, partials, lo);
+    else msm_reduce_segments<<<grid, block, 0, ctx->stream>>>(buckets, K, L, partials, lo);
     CAPGPU_LAUNCH_CHECK(ctx);
   }
   if (pair) msm_finalize_pair<<<(unsigned)batch, 32, 0, ctx->stream>>>(partials, nblocks, out_dev);
@@ -774,15 +808,7 @@ static int srs_create(capgpu_ctx* ctx, const uint64_t* points_xy, const uint64_t
   int rc = guarded(ctx, [&] {
     CAPGPU_REQUIRE(n_points >= 1 && n_points <= ((size_t)1 << 21), "SRS size out of range");
     int c = window_bits;
-    if (c == 0) {
-      c = ceil_log2(n_points) + 1;
-      if (c > 16) c = 16;
-      if (c < 4) c = 4;
-      // 2^12..2^14 points: a lone MSM is latency-bound (bucket chains, then the reduction), and many
-      // short buckets beat few long ones: measured 0.71 -> 0.46 ms (2^12), 0.62 -> 0.49 ms (2^13)
-      if (n_points >= ((size_t)1 << 12) && c < 15) c = 15;
-      if (const char* e = getenv("CAPGPU_WINDOW_BITS")) { int v = atoi(e); if (v >= 2 && v <= 16 && v < c) c = v; }
-    }
+    if (c == 0) c = choose_window(n_points);
     CAPGPU_REQUIRE(c >= 2 && c <= 16, "window_bits must be in [2, 16]");
     srs->device = ctx->device;
     srs->n = n_points;
@@ -891,9 +917,7 @@ capgpu_srs* srs_lagrange(capgpu_ctx* ctx, const capgpu_srs* srs, unsigned log_n,
   capgpu_srs* lag = new capgpu_srs();
   G1XYZZ* A = nullptr;
   try {
-    int c = ceil_log2(np) + 1;
-    if (c > 16) c = 16;
-    if (c < 4) c = 4;
+    int c = choose_window(np);
     lag->device = ctx->device;
     lag->n = np;
     lag->c = c;
@@ -954,6 +978,14 @@ extern "C" int capgpu_msm_g1_dev(capgpu_ctx* ctx, const capgpu_srs* srs, size_t 
   if (!ctx || !srs || !d_out_xy || (!d_scalars && n)) return CAPGPU_ERR_ARG;
   return guarded(ctx, [&] {
     msm_device(ctx, srs, base_off, (const Fr*)d_scalars, n, n, batch, scalars_mont != 0, (G1Affine*)d_out_xy, true);
+  });
+}
+
+extern "C" int capgpu_msm_g1_dev_part(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const void* d_scalars, size_t n,
+                                      int scalars_mont, size_t part, size_t parts, void* d_out_xy) {
+  if (!ctx || !srs || !d_out_xy || (!d_scalars && n)) return CAPGPU_ERR_ARG;
+  return guarded(ctx, [&] {
+    msm_device(ctx, srs, base_off, (const Fr*)d_scalars, n, n, 1, scalars_mont != 0, (G1Affine*)d_out_xy, true, part, parts);
   });
 }
 

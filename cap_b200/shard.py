@@ -31,37 +31,63 @@ def reduce_timing(ms: float, count: int, device=None, backend_tensor="cpu"):
     return float(t.item()), int(c.item())
 
 
-# ---- one large MSM split by point range -----------------------------------------------------
+# ---- one large MSM split across the GPUs of a box -----------------------------------------------
 def point_range(n_points: int, world: int, rank: int) -> tuple[int, int]:
-    """[lo, hi) slice of the bases (and scalars) that rank `rank` owns."""
+    """[lo, hi) slice of the bases (and scalars) that rank `rank` owns in a point-range split."""
     lo = n_points * rank // world
     hi = n_points * (rank + 1) // world
     return lo, hi
 
 
-def split_msm(ctx, srs_local, d_scalars_local, mont: bool = False):
-    """sum_i s_i P_i with bases / scalars sharded by point range across the ranks of the default
-    process group.  Each rank runs the MSM of its slice on its own GPU (`srs_local` holds only the
-    slice's bases, `d_scalars_local` is a CUDA int64 tensor of shape (n_local, 4)), the 64-byte
-    affine partial results are exchanged with ONE NCCL all-gather over NVLink, and every rank folds
-    them with EC additions on its GPU.  Returns a CUDA int64 tensor (8,) = x || y of the result."""
-    import torch
-    import torch.distributed as dist
-    from ctypes import c_void_p
-    from . import _lib
-    lib = ctx.lib
-    n_local = int(d_scalars_local.shape[0])
-    part = torch.zeros(8, dtype=torch.int64, device=d_scalars_local.device)
-    _lib.check(lib.capgpu_msm_g1_dev(ctx.h, srs_local.h, 0, c_void_p(d_scalars_local.data_ptr()), n_local, 1, int(mont),
-                                     c_void_p(part.data_ptr())), ctx.h)
-    ctx.sync()
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-        return part
-    world = dist.get_world_size()
-    gathered = torch.empty((world, 8), dtype=torch.int64, device=part.device)
-    dist.all_gather_into_tensor(gathered, part)
-    torch.cuda.current_stream().synchronize()
-    out = torch.zeros(8, dtype=torch.int64, device=part.device)
-    _lib.check(lib.capgpu_g1_sum_dev(ctx.h, c_void_p(gathered.data_ptr()), world, c_void_p(out.data_ptr())), ctx.h)
-    ctx.sync()
-    return out
+def bucket_parts(world: int) -> int:
+    """Bucket-range slices for `world` ranks: the largest power of two <= world (the bucket count
+    2^(c-1) is a power of two; ranks beyond it hold an empty slice and contribute infinity)."""
+    p = 1
+    while p * 2 <= world:
+        p *= 2
+    return p
+
+
+class SplitMsm:
+    """sum_i s_i P_i for ONE scalar vector, split across the ranks of the default process group by
+    BUCKET RANGE (BASELINE north_star: "a single large MSM can be split ... with partial sums reduced
+    over NVLink").  Every rank holds the whole commit key `srs` and the whole scalar vector; rank r
+    sorts, accumulates and reduces only the buckets of slice r (capgpu_msm_g1_dev_part), so all three
+    phases shrink with the number of GPUs.  The 64-byte slice results are exchanged with one NCCL
+    all-gather and folded with EC additions (capgpu_g1_sum_dev).  Everything -- the MSM kernels, the
+    all-gather and the fold -- is enqueued on the context's stream (it is made torch's current stream
+    for the collective), with no host synchronisation in between; the caller synchronises once."""
+
+    def __init__(self, ctx, srs):
+        import torch
+        import torch.distributed as dist
+        self.ctx, self.srs = ctx, srs
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank() if self.world > 1 else 0
+        self.parts = bucket_parts(self.world)
+        self.stream = torch.cuda.ExternalStream(ctx.stream)
+        dev = torch.device("cuda", ctx.device)
+        self.part = torch.zeros(8, dtype=torch.int64, device=dev)
+        self.gathered = torch.zeros((self.world, 8), dtype=torch.int64, device=dev)
+        self.out = torch.zeros(8, dtype=torch.int64, device=dev)
+
+    def __call__(self, d_scalars, mont: bool = False):
+        """d_scalars: CUDA int64 tensor (n, 4) on the context's GPU, identical on every rank.  Returns
+        a CUDA int64 tensor (8,) = x || y of the result (valid after ctx.sync())."""
+        import torch
+        import torch.distributed as dist
+        from ctypes import c_void_p
+        from . import _lib
+        lib, ctx = self.ctx.lib, self.ctx
+        n = int(d_scalars.shape[0])
+        if self.rank < self.parts:
+            _lib.check(lib.capgpu_msm_g1_dev_part(ctx.h, self.srs.h, 0, c_void_p(d_scalars.data_ptr()), n, int(mont), self.rank, self.parts,
+                                                  c_void_p(self.part.data_ptr())), ctx.h)
+        if self.world == 1:
+            return self.part
+        with torch.cuda.stream(self.stream):
+            if self.rank >= self.parts:
+                self.part.zero_()
+            dist.all_gather_into_tensor(self.gathered, self.part)
+        _lib.check(lib.capgpu_g1_sum_dev(ctx.h, c_void_p(self.gathered.data_ptr()), self.world, c_void_p(self.out.data_ptr())), ctx.h)
+        return self.out

@@ -101,6 +101,16 @@ int capgpu_msm_g1(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const
 int capgpu_msm_g1_dev(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const void* d_scalars, size_t n,
                       size_t batch, int scalars_mont, void* d_out_xy);
 
+/* One BUCKET-RANGE slice of an MSM, for splitting a single large MSM across the GPUs of a box
+ * (BASELINE north_star: "a single large MSM can be split ... with partial sums reduced over NVLink").
+ * Every GPU holds the whole commit key and the whole scalar vector; GPU `part` of `parts` keeps only
+ * the signed digits whose magnitude falls in its 1/parts of the 2^(c-1) buckets, so its sort,
+ * bucket accumulation AND bucket reduction all shrink by `parts`; the slice results are affine points
+ * whose sum (capgpu_g1_sum_dev after a gather over NVLink) is the MSM.  parts must divide 2^(c-1)
+ * (any power of two up to 8 does for every key of 16 points or more).  Asynchronous on the ctx stream. */
+int capgpu_msm_g1_dev_part(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const void* d_scalars, size_t n,
+                           int scalars_mont, size_t part, size_t parts, void* d_out_xy);
+
 /* MSM over bases that are not a resident SRS: sum_i scalars[i] * points[i] for n affine points
  * given by the caller (x || y Montgomery, all-zero = infinity).  This is the G1 work of the
  * batched verifier (`txn_batch_verify`, /root/reference/src/lib.rs:517, benches/batch_verification.rs:
@@ -172,6 +182,36 @@ typedef struct capgpu_proof {
   uint64_t wire_sigma_evals[4][4];
   uint64_t perm_next_eval[4];
 } capgpu_proof;
+
+/* ---- the reference's on-disk formats ----------------------------------------------
+ * `UniversalSrs` and the note proving keys are stored as ark-serialize 0.3 `CanonicalSerialize`
+ * blobs (`store_data` / `load_data`, /root/reference/src/parameters.rs:557-592); the Aztec CRS is
+ * deserialised behind a SHA-256 gate (/root/reference/src/proof/mod.rs:98-107).  These entry points
+ * take the file bytes as they are; the byte grammar is documented at the top of
+ * cap_b200/csrc/formats.cu and in INTEGRATION.md.  A blob that does not parse exactly is refused
+ * with CAPGPU_ERR_ARG (capgpu_last_error names the field).
+ *
+ * capgpu_srs_load_serialized: `UniversalSrs::deserialize(bytes)` + `trim`: expect_sha256 (32 bytes or
+ *   NULL) is checked first, like the reference's `assert_eq!(hasher.finalize(), hex!(..))`; only the
+ *   first max_points powers are kept (0 = all); points are decompressed on the device.
+ * capgpu_pk_load_serialized: `ProvingKey::deserialize(bytes)`: builds the key AND its commit key (the
+ *   `powers_of_g` embedded in the blob; owned by the key).  `consumed` (optional) receives the number
+ *   of bytes the key took -- CAP's `TransferProvingKey` / `MintProvingKey` / `FreezeProvingKey`
+ *   (src/proof/transfer.rs:60, mint.rs:55, freeze.rs:47) append n_inputs / n_outputs / tree_depth after
+ *   it; with consumed == NULL trailing bytes are an error.
+ * capgpu_proof_serialize: the `CanonicalSerialize` bytes of jf-plonk's `Proof` for a capgpu_proof
+ *   (out == NULL: size query). */
+int capgpu_sha256(const uint8_t* data, size_t len, uint8_t out[32]);
+int capgpu_srs_load_serialized(capgpu_ctx* ctx, const uint8_t* bytes, size_t len, const uint8_t* expect_sha256, size_t max_points,
+                               int window_bits, capgpu_srs** out);
+int capgpu_pk_load_serialized(capgpu_ctx* ctx, const uint8_t* bytes, size_t len, size_t* consumed, capgpu_pk** out);
+int capgpu_proof_serialize(const capgpu_proof* proof, uint8_t* out, size_t cap, size_t* len);
+/* The blinding scalars a prover draws, from the raw `next_u64` words of its RNG in draw order, the
+ * way ark-ff 0.3 `Fr::rand` consumes them (4 words per attempt, top two bits cleared, rejected if
+ * >= r; the accepted limbs are the Montgomery representation).  Used to replay a recorded proof
+ * (rust/parity-dump): out receives n_out x 4 uint64_t, *used the number of words consumed;
+ * CAPGPU_ERR_ARG if the words run out. */
+int capgpu_fr_rand_from_words(const uint64_t* words, size_t n_words, uint64_t* out, size_t n_out, size_t* used);
 
 /* ---- whole proof -----------------------------------------------------------------------------
  * Replaces `PlonkKzgSnark::prove::<_, _, SolidityTranscript>(rng, &circuit, &pk, Some(ext_msg))`.

@@ -137,12 +137,13 @@ def preprocess(circ, srs=None, tau=None):
 
 
 # ----------------------------------------------------------------------------- prover
-def grand_product(circ, beta, gamma):
-    """jf-relation ``compute_prod_permutation_polynomial`` evaluations z_0..z_{n-1}."""
+def grand_product(circ, beta, gamma, w=None, sig=None):
+    """jf-relation ``compute_prod_permutation_polynomial`` evaluations z_0..z_{n-1}.  ``w`` / ``sig``:
+    witness columns / sigma evaluations when they come from a recorded proof instead of ``circ``."""
     n = circ.n
-    w = wire_evals(circ)
+    w = wire_evals(circ) if w is None else w
     ext = extended_id_permutation(circ)
-    sig = sigma_evals(circ)
+    sig = sigma_evals(circ) if sig is None else sig
     z = [1]
     for j in range(n - 1):
         a = 1
@@ -193,19 +194,24 @@ def quotient_evals(circ, pk, wire_polys, z_poly, pi_poly, beta, gamma, alpha):
 def prove(circ, pk, blinders, srs=None, tau=None, ext_msg: bytes | None = None, keep=False):
     """Returns the proof dict (13 G1 + 10 Fr).  ``blinders``: 17 canonical Fr values in the
     order the prover draws them: wires 0..4 (2 each), z (3), split-quotient maskers (4)."""
+    return prove_with_columns(circ, pk, wire_evals(circ), public_input(circ), blinders, srs=srs, tau=tau, ext_msg=ext_msg, keep=keep)
+
+
+def prove_with_columns(circ, pk, w_ev, pub, blinders, srs=None, tau=None, ext_msg: bytes | None = None, keep=False):
+    """The prover on explicit witness columns (5 x n values) and public inputs -- what a recorded
+    proof (tests/test_replay.py) provides.  ``circ`` only supplies n, log_n and k; the permutation
+    enters through ``pk["sigma_evals"]``."""
     assert len(blinders) == 17
     n = circ.n
     log_n = circ.log_n
     omega = fr_root_of_unity(log_n)
     vk = pk["vk"]
-    pub = public_input(circ)
     tr = SolidityTranscript()
     if ext_msg is not None:
         tr.append_message(ext_msg)
     tr.append_vk_and_pub_input(vk, pub)
 
     # Round 1
-    w_ev = wire_evals(circ)
     wire_polys = [mask_polynomial(ifft(w_ev[i], log_n), blinders[2 * i:2 * i + 2], n) for i in range(NUM_WIRES)]
     wire_comms = [commit(p, srs, tau) for p in wire_polys]
     pi_poly = ifft(pub + [0] * (n - len(pub)), log_n)
@@ -214,7 +220,7 @@ def prove(circ, pk, blinders, srs=None, tau=None, ext_msg: bytes | None = None, 
     # Round 2
     beta = tr.get_and_append_challenge()
     gamma = tr.get_and_append_challenge()
-    z_ev = grand_product(circ, beta, gamma)
+    z_ev = grand_product(circ, beta, gamma, w_ev, pk["sigma_evals"])
     z_poly = mask_polynomial(ifft(z_ev, log_n), blinders[10:13], n)
     z_comm = commit(z_poly, srs, tau)
     tr.append_commitment(z_comm)

@@ -58,6 +58,7 @@ extern "C" {
     pub fn capgpu_srs_export(ctx: *mut capgpu_ctx, srs: *const capgpu_srs, points_xy: *mut u64, n_points: usize) -> c_int;
     pub fn capgpu_srs_size(srs: *const capgpu_srs) -> usize;
     pub fn capgpu_msm_g1_dev(ctx: *mut capgpu_ctx, srs: *const capgpu_srs, base_off: usize, d_scalars: *const c_void, n: usize, batch: usize, scalars_mont: c_int, d_out_xy: *mut c_void) -> c_int;
+    pub fn capgpu_msm_g1_dev_part(ctx: *mut capgpu_ctx, srs: *const capgpu_srs, base_off: usize, d_scalars: *const c_void, n: usize, scalars_mont: c_int, part: usize, parts: usize, d_out_xy: *mut c_void) -> c_int;
     pub fn capgpu_msm_g1_adhoc(ctx: *mut capgpu_ctx, points_xy: *const u64, scalars: *const u64, n: usize, scalars_mont: c_int, out_xy: *mut u64) -> c_int;
     pub fn capgpu_g1_sum_dev(ctx: *mut capgpu_ctx, d_points_xy: *const c_void, count: usize, d_out_xy: *mut c_void) -> c_int;
     pub fn capgpu_ntt_dev(ctx: *mut capgpu_ctx, d_in: *const c_void, in_len: usize, d_out: *mut c_void, log_n: c_uint, batch: usize, inverse: c_int, coset: c_int) -> c_int;
@@ -78,6 +79,13 @@ extern "C" {
     pub fn capgpu_poll(q: *mut capgpu_queue, ticket: u64, done: *mut c_int) -> c_int;
     pub fn capgpu_wait(q: *mut capgpu_queue, ticket: u64, out: *mut capgpu_proof) -> c_int;
     pub fn capgpu_queue_stats(q: *mut capgpu_queue, submitted: *mut u64, completed: *mut u64, groups: *mut u64, copy_ms: *mut f64, wait_slot_ms: *mut f64) -> c_int;
+
+    // the reference's on-disk formats, proof bytes, RNG replay
+    pub fn capgpu_sha256(data: *const u8, len: usize, out: *mut u8) -> c_int;
+    pub fn capgpu_srs_load_serialized(ctx: *mut capgpu_ctx, bytes: *const u8, len: usize, expect_sha256: *const u8, max_points: usize, window_bits: c_int, out: *mut *mut capgpu_srs) -> c_int;
+    pub fn capgpu_pk_load_serialized(ctx: *mut capgpu_ctx, bytes: *const u8, len: usize, consumed: *mut usize, out: *mut *mut capgpu_pk) -> c_int;
+    pub fn capgpu_proof_serialize(proof: *const capgpu_proof, out: *mut u8, cap: usize, len: *mut usize) -> c_int;
+    pub fn capgpu_fr_rand_from_words(words: *const u64, n_words: usize, out: *mut u64, n_out: usize, used: *mut usize) -> c_int;
 
     // diagnostics
     pub fn capgpu_debug_read(ctx: *mut capgpu_ctx, what: c_int, out: *mut u64, max_elems: usize, n_elems: *mut usize) -> c_int;

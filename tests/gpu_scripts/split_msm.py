@@ -1,10 +1,15 @@
-"""Dev / evidence script (torchrun, N >= 2 GPUs): one 2^17-point MSM split by point range across
-the ranks, partial results all-gathered over NCCL/NVLink and folded with EC additions; checked
-against p(tau) * G from the oracle and timed beside the single-GPU MSM."""
+"""torchrun script (N >= 2 GPUs): ONE MSM split by bucket range across the ranks (cap_b200.shard.
+SplitMsm: slice MSM kernels, NCCL all-gather of the 64-byte slice results and the EC fold all
+enqueued on the context stream), checked against p(tau) * G from the oracle and timed beside the
+single-GPU MSM.  Used by tests/test_gpu_primitives.py::test_split_msm_across_gpus and as evidence
+(gpurun_out/split_msm_<N>gpu.json):
+    torchrun --nproc-per-node N tests/gpu_scripts/split_msm.py [--points P] [--reps R]"""
+import argparse
 import json
 import os
 import statistics
 import sys
+from ctypes import c_void_p
 
 import numpy as np
 
@@ -12,60 +17,58 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspa
 import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
-from cap_b200 import device, field, shard  # noqa: E402
-from oracle import msm as omsm  # noqa: E402
+from cap_b200 import _lib, device, field, shard  # noqa: E402
+from oracle import msm as omsm  # noqa: E402  (checker)
 
+ap = argparse.ArgumentParser()
+ap.add_argument("--points", type=int, default=1 << 17)
+ap.add_argument("--reps", type=int, default=12)
+args = ap.parse_args()
 TAU = 0x2B7E151628AED2A6ABF7158809CF4F3C762E7160F38B4DA56A784D9045190CFE % field.R
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 ctx = device.Context(local)
-N = 1 << 17
-full = device.Srs(ctx, tau_mont=field.fr_to_mont_array([TAU])[0], size=N)
-lo, hi = shard.point_range(N, world, rank)
-local_srs = device.Srs(ctx, points_xy=full.export()[lo:hi])
+N = args.points
+srs = device.Srs(ctx, tau_mont=field.fr_to_mont_array([TAU])[0], size=N)  # the whole commit key on every GPU
 sc = np.random.default_rng(5).integers(0, 1 << 62, size=(N, 4), dtype=np.uint64)
 sc[:, 3] &= (1 << 60) - 1
 d_all = torch.from_numpy(sc.view(np.int64)).cuda()
-d_loc = d_all[lo:hi].contiguous()
+split = shard.SplitMsm(ctx, srs)
 
-res = shard.split_msm(ctx, local_srs, d_loc)
+res = split(d_all)
+ctx.sync()
 got = field.g1_from_mont_array(res.cpu().numpy().view(np.uint64))[0]
-ok = True
-if rank == 0:
-    ok = got == omsm.kzg_commit_tau(field.fr_from_raw_array(sc), TAU)
+ok = got == omsm.kzg_commit_tau(field.fr_from_raw_array(sc), TAU)
+oks = [None] * world
+dist.all_gather_object(oks, bool(ok))
 
 
-def timed(fn, reps=10):
+def timed(fn, reps):
+    """CUDA events on the context stream, max over ranks, median of reps (2 warm-ups dropped)."""
+    stream = torch.cuda.ExternalStream(ctx.stream)
     ts = []
-    for _ in range(reps):
+    for _ in range(reps + 2):
         dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
+        e0.record(stream)
         fn()
-        e1.record()
-        torch.cuda.synchronize()
+        e1.record(stream)
+        e1.synchronize()
         t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ts.append(float(t.item()))
     return statistics.median(ts[2:])
 
 
-split_ms = timed(lambda: shard.split_msm(ctx, local_srs, d_loc))
+split_ms = timed(lambda: split(d_all), args.reps)
 out1 = torch.zeros(8, dtype=torch.int64, device="cuda")
-from ctypes import c_void_p  # noqa: E402
-from cap_b200 import _lib  # noqa: E402
-
-
-def single():
-    _lib.check(ctx.lib.capgpu_msm_g1_dev(ctx.h, full.h, 0, c_void_p(d_all.data_ptr()), N, 1, 0, c_void_p(out1.data_ptr())), ctx.h)
-    ctx.sync()
-
-
-single_ms = timed(single)
+single_ms = timed(lambda: _lib.check(ctx.lib.capgpu_msm_g1_dev(ctx.h, srs.h, 0, c_void_p(d_all.data_ptr()), N, 1, 0, c_void_p(out1.data_ptr())), ctx.h),
+                  args.reps)
 if rank == 0:
-    line = {"n_gpus": world, "points": N, "split_msm_ms": split_ms, "single_gpu_msm_ms": single_ms, "correct": bool(ok)}
+    line = {"n_gpus": world, "points": N, "split": "bucket range", "bucket_parts": split.parts, "split_msm_ms": split_ms,
+            "single_gpu_msm_ms": single_ms, "speedup": single_ms / split_ms, "correct": all(oks)}
     print(json.dumps(line), flush=True)
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(line, open(f"gpurun_out/split_msm_{world}gpu.json", "w"))

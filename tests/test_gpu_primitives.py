@@ -1,6 +1,7 @@
 """GPU parity tests for the standalone primitives, through the C ABI (capgpu_ntt, capgpu_msm_g1):
 bit-exact against the oracle at sizes it finishes in seconds, golden fixtures, and
 size-independent properties at the benchmark sizes."""
+import os
 import random
 
 import numpy as np
@@ -234,3 +235,48 @@ def test_srs_upload_from_compressed_points(ctx):
     assert pow(3, (B.Q - 1) // 2, B.Q) == B.Q - 1
     with pytest.raises(_lib.CapGpuError):
         device.Srs(ctx, compressed=bytes(32))
+
+
+@pytest.mark.parametrize("log_n,parts", [(9, 2), (12, 8), (15, 8), (6, 4)])
+def test_msm_bucket_range_slices_sum_to_the_msm(ctx, log_n, parts):
+    """capgpu_msm_g1_dev_part: the bucket-range slices of one MSM (what each GPU of a split MSM
+    computes) add up to the whole MSM -- uniform scalars, and skewed ones that put every digit into
+    the first slice (small scalars) or the last (magnitudes near 2^(c-1))."""
+    import torch
+    from ctypes import c_void_p
+    n = (1 << log_n) + 3
+    srs = device.Srs(ctx, tau_mont=field.fr_to_mont_array([TAU])[0], size=n)
+    rng = np.random.default_rng(log_n)
+    uniform = rng.integers(0, 1 << 62, size=(n, 4), dtype=np.uint64)
+    uniform[:, 3] &= (1 << 60) - 1
+    small = np.zeros((n, 4), dtype=np.uint64)
+    small[:, 0] = rng.integers(0, 4, size=n, dtype=np.uint64)
+    for sc in (uniform, small):
+        want = srs.msm(sc, mont=False)
+        d = torch.from_numpy(sc.view(np.int64)).cuda()
+        outs = torch.zeros((parts, 8), dtype=torch.int64, device="cuda")
+        for p in range(parts):
+            _lib.check(ctx.lib.capgpu_msm_g1_dev_part(ctx.h, srs.h, 0, c_void_p(d.data_ptr()), n, 0, p, parts, c_void_p(outs[p].data_ptr())), ctx.h)
+        total = torch.zeros(8, dtype=torch.int64, device="cuda")
+        _lib.check(ctx.lib.capgpu_g1_sum_dev(ctx.h, c_void_p(outs.data_ptr()), parts, c_void_p(total.data_ptr())), ctx.h)
+        ctx.sync()
+        assert np.array_equal(total.cpu().numpy().view(np.uint64), want)
+    assert ctx.lib.capgpu_msm_g1_dev_part(ctx.h, srs.h, 0, c_void_p(d.data_ptr()), n, 0, 3, 3, c_void_p(total.data_ptr())) == -2
+    srs.close()
+
+
+def test_split_msm_across_gpus():
+    """The split MSM on every GPU of the box (torchrun, NCCL all-gather of the slice results
+    enqueued on the context stream): equals p(tau) G.  Skipped with fewer than 2 GPUs."""
+    import subprocess
+    import sys
+    import torch
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs at least 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={ngpu}", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(root, "tests", "gpu_scripts", "split_msm.py"), "--points", str(1 << 14), "--reps", "3"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    assert '"correct": true' in res.stdout

@@ -65,9 +65,13 @@ def test_point_range_partition():
             assert all(rs[i][1] == rs[i + 1][0] for i in range(world - 1))
 
 
+def test_bucket_parts():
+    assert [shard.bucket_parts(w) for w in (1, 2, 3, 4, 5, 8)] == [1, 2, 2, 4, 4, 8]
+
+
 def _split_worker(rank, world, port, q):
-    """Point-range split of one MSM: partial sums per rank (oracle arithmetic stands in for the
-    GPU here), one all-gather of the 64-byte results, EC fold on every rank."""
+    """Split of one MSM: partial sums per rank (oracle arithmetic stands in for the GPU here),
+    one all-gather of the 64-byte results, EC fold on every rank."""
     import random
     from oracle import bn254 as B
     from oracle import msm as omsm
