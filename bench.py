@@ -61,6 +61,7 @@ def parse_args():
     ap.add_argument("--no-lagrange", action="store_true", help="commit wire polynomials from coefficients (A/B against the evaluation-form path)")
     ap.add_argument("--fixture", default=None, help="CAPFIX01 replay fixture (rust/parity-dump): prove ITS key / witness / RNG words instead of the "
                                                      "synthetic workload and compare the proof bytes with the recorded ones")
+    ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE config 2-5 measurements (other note shapes, kernel sweeps, 1024-note batch)")
     ap.add_argument("--no-extras", action="store_true", help="skip roofline / MSM-latency / cpu_baseline side measurements")
     return ap.parse_args()
 
@@ -68,16 +69,16 @@ def parse_args():
 # --------------------------------------------------------------------------------------------
 # workload
 # --------------------------------------------------------------------------------------------
-def build_workload(name: str, witness: str = "dense"):
+def build_workload(name: str, witness: str = "dense", witnesses: int = N_WITNESSES):
     from cap_b200 import field, plonk, synth
     log_n, nin = synth.NOTE_SHAPES[name]
     kw = {"zero_inputs": 0.45, "bool_inputs": 0.5} if witness == "sparse" else {}
     circ = synth.make_circuit(log_n, num_inputs=nin, seed=7, **kw)
-    circs = [circ] + [circ.with_witness(s) for s in range(1, N_WITNESSES)]
+    circs = [circ] + [circ.with_witness(s) for s in range(1, witnesses)]
     wires = [plonk.wire_values(c) for c in circs]
     pubs = [field.fr_to_mont_array(plonk.public_input(c)) for c in circs]
     rng = np.random.default_rng(2022)
-    bl = rng.integers(0, 1 << 62, size=(N_WITNESSES, 17, 4), dtype=np.uint64)
+    bl = rng.integers(0, 1 << 62, size=(witnesses, 17, 4), dtype=np.uint64)
     bl[..., 3] &= (1 << 60) - 1  # Montgomery limbs of values < r, as Fr::rand returns them
     return circ, circs, wires, pubs, bl
 
@@ -456,6 +457,141 @@ def side_measurements(args, torch, ctxs, pk, srs, circ, wires_dev, wires, pubs, 
     # ---- CPU baseline: the C restatement of the reference's CPU algorithms on this host's cores
     if world == 1 and args.cpu_sample != 0:
         out["cpu_baseline"] = cpu_baseline(args, circ, pk, srs, wires, pubs, bl, args.cpu_sample)
+    # ---- BASELINE configs 2-5 (other note shapes, kernel sweeps, the 1024-note batch, batch verification)
+    if world == 1 and not args.no_configs:
+        out["configs"] = other_configs(args, torch, ctxs, calib, imad_peak)
+    return out
+
+
+def profile_group(lib, ctx, run_group, group: int):
+    """(per-proof kernel times, msm_accumulate roofline fraction) of one lockstep group run alone."""
+    from ctypes import byref, c_double, c_uint64
+    from cap_b200 import _lib
+    run_group()
+    _lib.check(lib.capgpu_profile_enable(ctx.h, 1), ctx.h)
+    run_group()
+    ms, cnt, units = c_double(), c_uint64(), c_double()
+    lib.capgpu_profile_read(ctx.h, 0, byref(ms), byref(cnt), byref(units))
+    _lib.check(lib.capgpu_profile_enable(ctx.h, 0), ctx.h)
+    gmad = units.value * MADD_F_MULS * F_MUL_WIDE_MADS / (ms.value * 1e-3) * 1e-9 if ms.value > 0 else 0.0
+    return ms.value / group, gmad
+
+
+def other_configs(args, torch, ctxs, calib, imad_peak):
+    """BASELINE.json configs 2-5 on this GPU, each with its own roofline fraction: MintNote / FreezeNote /
+    larger TransferNote shapes (proofs/s through capgpu_prove_batch_dev, lockstep groups), the standalone
+    MSM 2^12-2^17 and NTT 2^12-2^18 sweep against the C restatement on the host cores, the 1024-note batch
+    and the G1 sums of benches/batch_verification.rs."""
+    from ctypes import c_void_p
+    from cap_b200 import _lib, device, field, plonk
+    from oracle import cpu  # CPU baseline leg of the sweeps (checker / baseline only)
+    ctx = ctxs[0]
+    lib = ctx.lib
+    out = {}
+    threads = os.cpu_count() or 1
+    g = torch.Generator(device="cuda").manual_seed(3)
+
+    # -- note shapes ---------------------------------------------------------------------------------
+    shapes = {}
+    for name, batch in (("mint", 64), ("freeze_5", 32), ("transfer_3x5", 32), ("transfer_5x5", 16), ("transfer_2x2_batch_1024", 1024)):
+        workload = "transfer_2x2" if name.endswith("1024") else name
+        circ, circs, wires, pubs, bl = build_workload(workload, witnesses=2)
+        srs = plonk.PlonkKzgSnark.universal_setup(ctx, circ.n + 2, TAU)
+        pk = plonk.PlonkKzgSnark.preprocess(ctx, srs, circ)
+        dev = [torch.from_numpy(w.view(np.int64)).cuda() for w in wires]
+        ptrs = [dev[i % 2].data_ptr() for i in range(batch)]
+        pp, bb, mm = [pubs[i % 2] for i in range(batch)], [bl[i % 2] for i in range(batch)], [b"cfg"] * batch
+        plonk.prove_batch_raw(ctxs, pk, ptrs, pp, bb, mm, on_device=True)  # warm-up: workspaces, tables
+        torch.cuda.synchronize()
+        steps = 1 if batch >= 1024 else 3
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            plonk.prove_batch_raw(ctxs, pk, ptrs, pp, bb, mm, on_device=True)
+        dt = time.perf_counter() - t0
+        gsz = args.group
+        ms_acc, gmad = profile_group(lib, ctx, lambda: plonk.prove_batch_raw(ctxs[:1], pk, ptrs[:gsz], pp[:gsz], bb[:gsz], mm[:gsz], on_device=True), gsz)
+        shapes[name] = {"domain": f"2^{circ.log_n}", "public_inputs": circ.num_inputs, "notes_per_step": batch, "steps": steps,
+                        "proofs_per_s": batch * steps / dt, "ms_per_proof": dt / (batch * steps) * 1e3,
+                        "msm_accumulate_ms_per_proof": ms_acc, "roofline_frac": gmad / imad_peak if imad_peak else None}
+        pk.close()
+        srs.close()
+        del dev
+    out["note_shapes"] = shapes
+
+    # -- standalone sweeps: GPU (device-resident, CUDA events on the ctx stream) vs the C restatement ----
+    stream = torch.cuda.ExternalStream(ctx.stream)
+
+    def gpu_ms(fn, reps=8):
+        fn()
+        ctx.sync()
+        ts = []
+        for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            fn()
+            e1.record(stream)
+            e1.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return statistics.median(ts)
+
+    def cpu_ms(fn, reps=2):
+        best = 1e30
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            best = min(best, time.perf_counter() - t0)
+        return best * 1e3
+
+    def ark_window(n):  # ark-ec 0.3 variable_base: c = ln_without_floats(n) + 2
+        lg = max(n - 1, 1).bit_length()
+        return 3 if n < 32 else lg * 69 // 100 + 2
+
+    msm_rows, ntt_rows = [], []
+    srs_big = device.Srs(ctx, tau_mont=field.fr_to_mont_array([TAU % field.R])[0], size=1 << 17)
+    pts_big = srs_big.export()
+    srs_big.close()
+    for lg in range(12, 18):
+        n = 1 << lg
+        srs = device.Srs(ctx, points_xy=pts_big[:n])
+        sc = torch.randint(-(1 << 63), (1 << 63) - 1, (n, 4), dtype=torch.int64, device="cuda", generator=g)
+        sc[:, 3] &= (1 << 60) - 1
+        res = torch.zeros(8, dtype=torch.int64, device="cuda")
+        ms = gpu_ms(lambda: _lib.check(lib.capgpu_msm_g1_dev(ctx.h, srs.h, 0, c_void_p(sc.data_ptr()), n, 1, 0, c_void_p(res.data_ptr())), ctx.h))
+        sc_h = sc.cpu().numpy().view(np.uint64)
+        want = cpu.msm(pts_big[:n], sc_h, mont=False, nthreads=threads)
+        c_ms = cpu_ms(lambda: cpu.msm(pts_big[:n], sc_h, mont=False, nthreads=threads))
+        c_ark = ark_window(n)
+        w_ark = (254 + c_ark - 1) // c_ark
+        ref_wide = (10 * n * w_ark + 28 * (1 << (c_ark - 1)) * w_ark) * F_MUL_WIDE_MADS  # SURVEY 8(d) formula at arkworks' (c, W)
+        msm_rows.append({"points": f"2^{lg}", "gpu_ms": ms, "cpu_ms": c_ms, "speedup": c_ms / ms, "bit_exact_vs_cpu": bool(np.array_equal(res.cpu().numpy().view(np.uint64), want)),
+                         "frac_of_imad_roofline_survey_formula": ref_wide / (ms * 1e-3) * 1e-9 / imad_peak})
+        srs.close()
+    for lg in range(12, 19):
+        n = 1 << lg
+        a = torch.randint(0, 1 << 60, (n, 4), dtype=torch.int64, device="cuda", generator=g)
+        b = torch.empty_like(a)
+        ms = gpu_ms(lambda: _lib.check(lib.capgpu_ntt_dev(ctx.h, c_void_p(a.data_ptr()), n, c_void_p(b.data_ptr()), lg, 1, 0, 0), ctx.h))
+        a_h = a.cpu().numpy().view(np.uint64)
+        want = cpu.ntt(a_h, lg, nthreads=threads)
+        c_ms = cpu_ms(lambda: cpu.ntt(a_h, lg, nthreads=threads))
+        ntt_rows.append({"size": f"2^{lg}", "gpu_ms": ms, "cpu_ms": c_ms, "speedup": c_ms / ms, "bit_exact_vs_cpu": bool(np.array_equal(b.cpu().numpy().view(np.uint64), want)),
+                         "frac_of_fmul_microbench": (n / 2) * lg / (ms * 1e-3) * 1e-9 / calib["gfmul_per_s"],
+                         "algorithmic_gbs": 2 * 32 * n / (ms * 1e-3) * 1e-9})
+    out["msm_sweep"] = msm_rows
+    out["ntt_sweep"] = ntt_rows
+
+    # -- benches/batch_verification.rs: the aggregated commitment sum of 1024 proofs of one note type
+    # (18 + 13 * 1024 bases supplied per call), host buffers in, affine point out
+    nb = 18 + 13 * 1024
+    pts = pts_big[:nb]
+    sc = np.random.default_rng(11).integers(0, 1 << 62, size=(nb, 4), dtype=np.uint64)
+    sc[:, 3] &= (1 << 60) - 1
+    got = device.msm_adhoc(ctx, pts, sc, mont=False)
+    t_gpu = cpu_ms(lambda: device.msm_adhoc(ctx, pts, sc, mont=False), reps=3)
+    want = cpu.msm(pts, sc, mont=False, nthreads=threads)
+    t_cpu = cpu_ms(lambda: cpu.msm(pts, sc, mont=False, nthreads=threads))
+    out["batch_verification_g1_sum_1024_proofs"] = {"bases": nb, "gpu_ms_host_to_host": t_gpu, "cpu_ms": t_cpu, "cpu_threads": threads,
+                                                    "bit_exact_vs_cpu": bool(np.array_equal(got, want))}
     return out
 
 

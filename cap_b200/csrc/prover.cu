@@ -95,7 +95,9 @@ struct NvtxRange {
 
 size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-capgpu_job* job_acquire(capgpu_ctx* ctx, const capgpu_pk* pk, int G) {
+// cap_hint: capacity to allocate if the workspace has to be (re)built -- the batch paths pass the
+// context's group size so that a first, smaller group does not cause a second allocation later
+capgpu_job* job_acquire(capgpu_ctx* ctx, const capgpu_pk* pk, int G, int cap_hint = 1) {
   CAPGPU_REQUIRE(pk->device == ctx->device, "proving key lives on another device");
   CAPGPU_REQUIRE(G >= 1 && G <= CAPGPU_MAX_GROUP, "group size out of range");
   capgpu_job* job = ctx->cached_job;
@@ -108,13 +110,13 @@ capgpu_job* job_acquire(capgpu_ctx* ctx, const capgpu_pk* pk, int G) {
     std::unique_ptr<capgpu_job, void (*)(capgpu_job*)> holder(new capgpu_job(), capgpu_job_free_internal);
     job = holder.get();
     job->ctx = ctx;
-    job->cap = G;
+    job->cap = G > cap_hint ? G : cap_hint;
     job->n = pk->n;
     job->m = pk->m;
     job->NP = pk->n + 8;
     job->num_inputs = pk->num_inputs;
     job->pub_stride = align_up(pk->num_inputs + 1, 8);
-    const size_t n = job->n, m = job->m, NP = job->NP, C = (size_t)G;
+    const size_t n = job->n, m = job->m, NP = job->NP, C = (size_t)job->cap;
     job->cstride = n / 8 + 8;
     job->div_tmax = (NP + 15) / 16 + 1;
     const size_t elems = C * (6 * NP + 7 * NP + n + 7 * m + m + 5 * NP + 4 * NP + 2 * n + 2 * job->cstride + 7 * m + 16 + 160 +
@@ -622,8 +624,8 @@ namespace capgpu {
 // (the whole group fails).  `inputs_consumed` (optional) is called once the wire values have been
 // read from the callers' buffers (end of round 1).
 void prove_group(capgpu_ctx* ctx, const capgpu_pk* pk, int G, const NoteIn* notes, capgpu_proof* const* out, int* status,
-                 const std::function<void()>& inputs_consumed) {
-  capgpu_job* job = job_acquire(ctx, pk, G);
+                 const std::function<void()>& inputs_consumed, int cap_hint) {
+  capgpu_job* job = job_acquire(ctx, pk, G, cap_hint);
   struct Release { capgpu_job* j; ~Release() { j->busy = false; } } release{job};
   job_begin(job, notes);
   std::vector<SolidityTranscript> tr(G);
@@ -693,7 +695,7 @@ static int prove_impl(capgpu_ctx* ctx, const capgpu_pk* pk, const uint64_t* wire
   int status = CAPGPU_OK;
   int rc = guarded(ctx, [&] {
     NoteIn in{wires, wires_on_device, pub_inputs, blinders, ext_msg, ext_msg_len};
-    prove_group(ctx, pk, 1, &in, &out, &status, nullptr);
+    prove_group(ctx, pk, 1, &in, &out, &status, nullptr, 1);
   });
   return rc != CAPGPU_OK ? rc : status;
 }
@@ -736,8 +738,12 @@ static int prove_batch_impl(capgpu_ctx* const* ctxs, size_t n_ctxs, const capgpu
       {
         std::lock_guard<std::mutex> lk(mu);
         if (next >= count) break;
-        const size_t left = count - next, share = (left + n_ctxs - 1) / n_ctxs;
-        take = (size_t)ctx->group < share ? (size_t)ctx->group : share;
+        // an even share of what is left, but no group smaller than half the lockstep size (small groups
+        // pay the five host round trips for little work)
+        const size_t left = count - next, share = (left + n_ctxs - 1) / n_ctxs, G = (size_t)ctx->group;
+        take = share < (G + 1) / 2 ? (G + 1) / 2 : share;
+        if (take > G) take = G;
+        if (take > left) take = left;
         i0 = next;
         next += take;
       }
@@ -751,7 +757,7 @@ static int prove_batch_impl(capgpu_ctx* const* ctxs, size_t n_ctxs, const capgpu
                           (ext_msgs && ext_msg_lens && ext_msgs[i]) ? ext_msg_lens[i] : 0};
         outs[g] = &out[i];
       }
-      int rc = guarded(ctx, [&] { prove_group(ctx, pk, g_n, notes.data(), outs.data(), st.data(), nullptr); });
+      int rc = guarded(ctx, [&] { prove_group(ctx, pk, g_n, notes.data(), outs.data(), st.data(), nullptr, ctx->group); });
       for (int g = 0; g < g_n; g++) {
         const int code = rc != CAPGPU_OK ? rc : st[g];
         if (status) status[i0 + g] = code;
@@ -832,7 +838,9 @@ struct capgpu_queue {
         }
         // leave work for the other contexts: never more than an even share of what is pending
         const size_t share = (pending.size() + ctxs.size() - 1) / ctxs.size();
-        const size_t take = share < G ? share : G;
+        size_t take = share < (G + 1) / 2 ? (G + 1) / 2 : share;
+        if (take > G) take = G;
+        if (take > pending.size()) take = pending.size();
         for (size_t i = 0; i < take; i++) { grp.push_back(pending.front()); pending.pop_front(); grp.back()->state = 1; }
         groups++;
       }
@@ -856,7 +864,7 @@ struct capgpu_queue {
         for (Note* nt : grp) { free_slots.push_back(nt->slot); nt->slot = -1; }
         cv_slot.notify_all();
       };
-      int rc = guarded(ctx, [&] { prove_group(ctx, pk, g_n, in.data(), outs.data(), st.data(), release_slots); });
+      int rc = guarded(ctx, [&] { prove_group(ctx, pk, g_n, in.data(), outs.data(), st.data(), release_slots, ctx->group); });
       release_slots();
       {
         std::lock_guard<std::mutex> lk(mu);

@@ -39,7 +39,7 @@ struct NoteIn {
 };
 
 void prove_group(capgpu_ctx* ctx, const capgpu_pk* pk, int G, const NoteIn* notes, capgpu_proof* const* out, int* status,
-                 const std::function<void()>& inputs_consumed);
+                 const std::function<void()>& inputs_consumed, int cap_hint);
 
 int pk_create_from_coefficients(capgpu_ctx* ctx, const capgpu_srs* srs, unsigned log_n, size_t num_inputs, const uint64_t* selectors,
                                 const uint64_t* sigmas, const uint64_t* k, const uint64_t* selector_comms_xy,

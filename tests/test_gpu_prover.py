@@ -437,7 +437,7 @@ def test_lagrange_and_coefficient_commitments_agree_on_sparse_witness(ctx):
     srs.close()
 
 
-@pytest.mark.parametrize("shape", ["mint", "transfer_2x2", "transfer_3x5", "transfer_5x5"])
+@pytest.mark.parametrize("shape", ["mint", "transfer_2x2", "transfer_3x5", "freeze_5", "transfer_5x5"])
 def test_note_shapes_match_the_c_restatement_at_full_size(ctx, shape):
     """BASELINE configs 1-3 (n = 2^14 .. 2^17): key and proof from the GPU equal, byte for byte, what the C
     restatement of the arkworks / jf-plonk algorithms computes on the CPU from the same SRS, circuit,
