@@ -54,6 +54,7 @@ extern "C" void capgpu_ctx_destroy(capgpu_ctx* ctx) {
   ctx->msm_scalars.release(); ctx->msm_digits.release(); ctx->msm_counts.release();
   ctx->msm_entries.release(); ctx->msm_buckets.release(); ctx->msm_partials.release(); ctx->msm_out.release();
   ctx->msm_flat.release();
+  ctx->msm_ticket.release();
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->sync_ev) cudaEventDestroy(ctx->sync_ev);
   if (ctx->pe0) cudaEventDestroy(ctx->pe0);

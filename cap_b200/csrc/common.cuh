@@ -61,6 +61,7 @@ struct capgpu_ctx {
   capgpu::DevBuf ntt_tmp, ntt_io;
   capgpu::DevBuf msm_scalars, msm_digits, msm_counts, msm_entries, msm_buckets, msm_partials, msm_out;
   capgpu::DevBuf msm_flat;  // chunk partials of the flat (low-latency) accumulation
+  capgpu::DevBuf msm_ticket;  // per-vector arrival counters of msm_red_planes (zero between launches)
   cudaEvent_t sync_ev = nullptr;  // cudaEventBlockingSync: host threads sleep while a round runs
   void* pinned = nullptr;  // small pinned staging area
   size_t pinned_bytes = 0;

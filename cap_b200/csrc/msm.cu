@@ -24,6 +24,7 @@
 // round) share every launch.  Also here: SRS upload paths (affine, compressed, synthetic tau),
 // the Lagrange commit key (group inverse DFT) and the ad-hoc-bases entry point.
 #include "common.cuh"
+#include "msm_reduce.cuh"
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
@@ -107,10 +108,14 @@ __global__ void msm_decompress(const uint32_t* __restrict__ bytes, G1Affine* tab
 // ------------------------------------------------------------------------------------------
 // recode + histogram
 // ------------------------------------------------------------------------------------------
-__global__ void msm_recode(const Fr* scalars, size_t n, size_t stride, int mont, int c, int W, int32_t* digits,
-                           uint32_t* counts, size_t K, uint32_t lo) {
-  // K buckets are handled by this launch: magnitudes lo + 1 .. lo + K (a bucket-range slice of a
-  // split MSM; lo = 0 and K = 2^(c-1) otherwise); digits outside the slice are dropped here
+// K buckets are handled by this launch: magnitudes lo + 1 .. lo + K (a bucket-range slice of a split MSM;
+// lo = 0 and K = 2^(c-1) otherwise); digits outside the slice are dropped here.  The histogram atomic also
+// hands every entry its rank inside its bucket, so the scatter needs no second round of atomics:
+// position = bucket offset (after the scan) + rank.  WMAX > 0: windows unrolled (W <= WMAX), all the
+// atomics of a scalar in flight together before the first rank is stored.
+template <int WMAX>
+__global__ void msm_recode(const Fr* __restrict__ scalars, size_t n, size_t stride, int mont, int c, int W, int32_t* __restrict__ digits,
+                           uint32_t* __restrict__ ranks, uint32_t* counts, size_t K, uint32_t lo) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const size_t b = blockIdx.y;
@@ -120,13 +125,19 @@ __global__ void msm_recode(const Fr* scalars, size_t n, size_t stride, int mont,
   const int32_t half = 1 << (c - 1);
   int32_t carry = 0;
   uint32_t* cnt = counts + b * (K + 2);
-  for (int w = 0; w < W; w++) {
+  auto digit = [&](int w) {
     uint32_t off = (uint32_t)(w * c);
     uint32_t limb = off >> 5, sh = off & 31;
     uint32_t v = 0;
     if (limb < 8) {
-      v = s.v[limb] >> sh;
-      if (sh + c > 32 && limb + 1 < 8) v |= s.v[limb + 1] << (32 - sh);
+      // dynamic limb index without local memory
+      uint32_t lo_w = 0, hi_w = 0;
+#pragma unroll
+      for (int l = 0; l < 8; l++) {
+        if (l == (int)limb) { lo_w = s.v[l]; hi_w = l + 1 < 8 ? s.v[l + 1] : 0u; }
+      }
+      v = lo_w >> sh;
+      if (sh + c > 32) v |= hi_w << (32 - sh);
       v &= mask;
     }
     int32_t d = (int32_t)v + carry;
@@ -134,88 +145,137 @@ __global__ void msm_recode(const Fr* scalars, size_t n, size_t stride, int mont,
     if (d > half) { d -= (1 << c); carry = 1; }
     uint32_t mag = (uint32_t)(d < 0 ? -d : d);
     if (mag <= lo || mag > lo + K) d = 0;
-    digits[(b * W + w) * n + i] = d;
-    if (d != 0) atomicAdd(&cnt[mag - lo], 1u);
+    return d;
+  };
+  if (WMAX > 0) {
+    int32_t d[WMAX > 0 ? WMAX : 1];
+    uint32_t r[WMAX > 0 ? WMAX : 1];
+#pragma unroll
+    for (int w = 0; w < WMAX; w++) {
+      d[w] = 0; r[w] = 0;
+      if (w < W) {
+        d[w] = digit(w);
+        if (d[w] != 0) r[w] = atomicAdd(&cnt[(uint32_t)(d[w] < 0 ? -d[w] : d[w]) - lo], 1u);
+      }
+    }
+#pragma unroll
+    for (int w = 0; w < WMAX; w++) {
+      if (w < W) {
+        const size_t slot = (b * W + w) * n + i;
+        digits[slot] = d[w];
+        ranks[slot] = r[w];
+      }
+    }
+  } else {
+    for (int w = 0; w < W; w++) {
+      const int32_t d = digit(w);
+      const size_t slot = (b * W + w) * n + i;
+      digits[slot] = d;
+      if (d != 0) ranks[slot] = atomicAdd(&cnt[(uint32_t)(d < 0 ? -d : d) - lo], 1u);
+    }
   }
 }
 
-// counts[b][0..K] -> exclusive offsets in place (entry K+1 = total); cursors = copy.
-__global__ void msm_scan(uint32_t* counts, uint32_t* cursors, uint32_t* order, size_t K) {
+// counts[b][0..K+1] -> exclusive offsets in place (entry K+1 = total).  One CTA per vector; every thread
+// scans a contiguous run of counters, a block scan joins the runs.  Buckets holding >= heavy_thr entries
+// are listed in heavy[b][..] (count in nheavy[b]) for msm_accumulate_heavy.  With make_order the bucket
+// schedule of msm_accumulate is built too: ids sorted by population, fullest first (counting sort on the
+// clamped size), so that lanes of a warp walk buckets of (nearly) equal length and the tail of the
+// accumulation grid is made of the emptiest buckets.
+__global__ void __launch_bounds__(1024) msm_scan(uint32_t* counts, uint32_t* order, uint32_t* heavy, uint32_t* nheavy, size_t K,
+                                                 uint32_t heavy_thr, int make_order) {
+  extern __shared__ uint32_t sc[];  // the K + 2 counters of this vector (loaded and stored coalesced)
   __shared__ uint32_t warp_sums[32];
-  __shared__ uint32_t carry_s;
   __shared__ uint32_t hist[256];
+  __shared__ uint32_t nh;
   uint32_t* cnt = counts + (size_t)blockIdx.x * (K + 2);
-  uint32_t* cur = cursors + (size_t)blockIdx.x * (K + 2);
+  uint32_t* hv = heavy + (size_t)blockIdx.x * K;
   const size_t total = K + 2;
-  if (threadIdx.x == 0) carry_s = 0;
-  __syncthreads();
-  for (size_t base = 0; base < total; base += blockDim.x) {
-    size_t idx = base + threadIdx.x;
-    uint32_t v = (idx < K + 1) ? cnt[idx] : 0u;
-    // inclusive warp scan
-    uint32_t x = v;
-    for (int o = 1; o < 32; o <<= 1) {
-      uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-      if ((threadIdx.x & 31) >= o) x += y;
-    }
-    if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = x;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      uint32_t ws = (threadIdx.x < (blockDim.x >> 5)) ? warp_sums[threadIdx.x] : 0u;
-      uint32_t z = ws;
-      for (int o = 1; o < 32; o <<= 1) {
-        uint32_t y = __shfl_up_sync(0xffffffffu, z, o);
-        if (threadIdx.x >= o) z += y;
-      }
-      warp_sums[threadIdx.x] = z - ws;  // exclusive
-    }
-    __syncthreads();
-    uint32_t excl = carry_s + warp_sums[threadIdx.x >> 5] + x - v;
-    if (idx < total) { cnt[idx] = excl; cur[idx] = excl; }
-    __syncthreads();
-    if (threadIdx.x == blockDim.x - 1) carry_s = excl + v;
-    __syncthreads();
+  {  // K + 2 is even and so is every vector's first index: 8-byte accesses
+    const uint2* src = reinterpret_cast<const uint2*>(cnt);
+    uint2* dst = reinterpret_cast<uint2*>(sc);
+#pragma unroll 4
+    for (size_t i = threadIdx.x; i < total / 2; i += blockDim.x) dst[i] = src[i];
   }
-  // Bucket schedule: ids sorted by population, fullest first (counting sort on the clamped
-  // size).  Lanes of a warp then walk buckets of (nearly) equal length and the tail of the
-  // accumulation grid is made of the emptiest buckets.
+  if (threadIdx.x == 0) nh = 0;  // (entries 0 and K + 1 are zero: the histogram only touches 1 .. K)
+  __syncthreads();
+  const size_t per = (total + blockDim.x - 1) / blockDim.x;  // odd for K = 2^j >= 2048: conflict-free strides
+  const size_t i0 = (size_t)threadIdx.x * per;
+  const size_t i1 = i0 + per < total ? i0 + per : total;
+  uint32_t sum = 0;
+  for (size_t i = i0; i < i1; i++) sum += sc[i];
+  // exclusive block scan of the per-thread sums
+  uint32_t x = sum;
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+    if ((threadIdx.x & 31) >= o) x += y;
+  }
+  if ((threadIdx.x & 31) == 31) warp_sums[threadIdx.x >> 5] = x;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    uint32_t ws = (threadIdx.x < (blockDim.x >> 5)) ? warp_sums[threadIdx.x] : 0u;
+    uint32_t z = ws;
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t y = __shfl_up_sync(0xffffffffu, z, o);
+      if (threadIdx.x >= o) z += y;
+    }
+    warp_sums[threadIdx.x] = z - ws;  // exclusive
+  }
+  __syncthreads();
+  uint32_t run = warp_sums[threadIdx.x >> 5] + x - sum;
+  for (size_t i = i0; i < i1; i++) {
+    const uint32_t v = sc[i];
+    sc[i] = run;
+    run += v;
+    if (i >= 1 && i <= K && v >= heavy_thr) hv[atomicAdd(&nh, 1u)] = (uint32_t)(i - 1);
+  }
+  __syncthreads();
+  {
+    const uint2* src = reinterpret_cast<const uint2*>(sc);
+    uint2* dst = reinterpret_cast<uint2*>(cnt);
+#pragma unroll 4
+    for (size_t i = threadIdx.x; i < total / 2; i += blockDim.x) dst[i] = src[i];
+  }
+  if (threadIdx.x == 0) nheavy[blockIdx.x] = nh;
+  if (!make_order) return;
   uint32_t* ord = order + (size_t)blockIdx.x * K;
   for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
   __syncthreads();
   for (size_t k = threadIdx.x; k < K; k += blockDim.x) {
-    uint32_t sz = cnt[k + 2] - cnt[k + 1];
+    uint32_t sz = sc[k + 2] - sc[k + 1];
     atomicAdd(&hist[255u - (sz > 255u ? 255u : sz)], 1u);
   }
   __syncthreads();
   if (threadIdx.x < 32) {
     // exclusive scan of 256 bins by one warp (8 bins per lane)
-    uint32_t loc[8], sum = 0;
-    for (int j = 0; j < 8; j++) { loc[j] = hist[threadIdx.x * 8 + j]; sum += loc[j]; }
-    uint32_t x = sum;
+    uint32_t loc[8], s8 = 0;
+    for (int j = 0; j < 8; j++) { loc[j] = hist[threadIdx.x * 8 + j]; s8 += loc[j]; }
+    uint32_t z = s8;
     for (int o = 1; o < 32; o <<= 1) {
-      uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-      if (threadIdx.x >= o) x += y;
+      uint32_t y = __shfl_up_sync(0xffffffffu, z, o);
+      if (threadIdx.x >= o) z += y;
     }
-    uint32_t run = x - sum;
-    for (int j = 0; j < 8; j++) { hist[threadIdx.x * 8 + j] = run; run += loc[j]; }
+    uint32_t r2 = z - s8;
+    for (int j = 0; j < 8; j++) { hist[threadIdx.x * 8 + j] = r2; r2 += loc[j]; }
   }
   __syncthreads();
   for (size_t k = threadIdx.x; k < K; k += blockDim.x) {
-    uint32_t sz = cnt[k + 2] - cnt[k + 1];
+    uint32_t sz = sc[k + 2] - sc[k + 1];
     uint32_t pos = atomicAdd(&hist[255u - (sz > 255u ? 255u : sz)], 1u);
     ord[pos] = (uint32_t)k;
   }
 }
 
-__global__ void msm_scatter(const int32_t* digits, size_t n, int W, uint32_t* cursors, uint32_t* entries, size_t K,
-                            size_t table_n, size_t base_off, uint32_t lo) {
+__global__ void msm_scatter(const int32_t* digits, const uint32_t* __restrict__ ranks, size_t n, int W, const uint32_t* __restrict__ offsets,
+                            uint32_t* entries, size_t K, size_t table_n, size_t base_off, uint32_t lo) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const size_t w = blockIdx.y, b = blockIdx.z;
-  int32_t d = digits[(b * W + w) * n + i];
+  const size_t slot = (b * W + w) * n + i;
+  int32_t d = digits[slot];
   if (d == 0) return;
   uint32_t k = (d < 0 ? (uint32_t)(-d) : (uint32_t)d) - lo;
-  uint32_t pos = atomicAdd(&cursors[b * (K + 2) + k], 1u);
+  uint32_t pos = offsets[b * (K + 2) + k] + ranks[slot];
   uint32_t idx = (uint32_t)(w * table_n + base_off + i);
   entries[b * ((size_t)W * n) + pos] = idx | (d < 0 ? 0x80000000u : 0u);
 }
@@ -361,17 +421,17 @@ __global__ void msm_combine_flat(const uint32_t* __restrict__ offsets, G1XYZZ* b
 // c = 10, 12 — piles n/4 .. n/16 entries on buckets 1..4; the default sizes, c = 15 / 16, leave
 // 14 bits there.  Such buckets still take one CTA each: 2^16 points at c = 12 cost 1.5 ms.)
 __global__ void __launch_bounds__(128) msm_accumulate_heavy(const G1Affine* __restrict__ table, const uint32_t* __restrict__ entries,
-                                                            const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ order,
-                                                            G1XYZZ* buckets, size_t K, size_t entries_stride, uint32_t heavy_thr) {
+                                                            const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ heavy,
+                                                            const uint32_t* __restrict__ nheavy, G1XYZZ* buckets, size_t K,
+                                                            size_t entries_stride) {
   __shared__ G1XYZZ smem[32];
   const size_t b = blockIdx.y;
   const uint32_t* off = offsets + b * (K + 2);
   const uint32_t* ent = entries + b * entries_stride;
-  for (size_t slot = blockIdx.x; slot < K; slot += gridDim.x) {
-    const size_t bucket = order[b * K + slot];
+  const uint32_t nh = nheavy[b];
+  for (uint32_t slot = blockIdx.x; slot < nh; slot += gridDim.x) {
+    const size_t bucket = heavy[b * K + slot];
     const uint32_t start = off[bucket + 1], end = off[bucket + 2];
-    if (end - start < MSM_HEAVY) break;       // end of the schedule's ">= 255" class
-    if (end - start < heavy_thr) continue;    // (uniform per CTA) ordinary bucket of a densely filled vector
     G1XYZZ acc = G1XYZZ::inf();
     for (uint32_t e = start + threadIdx.x; e < end; e += blockDim.x) {
       uint32_t u = ent[e];
@@ -437,78 +497,6 @@ __global__ void __launch_bounds__(128) msm_reduce_segments(const G1XYZZ* __restr
 // latencies per addition instead of 14 (5 instead of 9 per doubling).  Same formulas, same
 // special cases (decided identically by both lanes).
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ Fq fq_sel(bool c, const Fq& a, const Fq& b) {
-  Fq r;
-#pragma unroll
-  for (int i = 0; i < 8; i++) r.v[i] = c ? a.v[i] : b.v[i];
-  return r;
-}
-__device__ __forceinline__ Fq fq_xchg(const Fq& a, uint32_t pmask) {
-  Fq r;
-#pragma unroll
-  for (int i = 0; i < 8; i++) r.v[i] = __shfl_xor_sync(pmask, a.v[i], 1);
-  return r;
-}
-// r0 = a0 * b0, r1 = a1 * b1; lane `role` of the pair computes product `role`
-__device__ __forceinline__ void pair_mul2(const Fq& a0, const Fq& b0, const Fq& a1, const Fq& b1, bool role, uint32_t pmask, Fq& r0,
-                                          Fq& r1) {
-  Fq m = fp_mul(fq_sel(role, a1, a0), fq_sel(role, b1, b0));
-  Fq o = fq_xchg(m, pmask);
-  r0 = fq_sel(role, o, m);
-  r1 = fq_sel(role, m, o);
-}
-
-__device__ __noinline__ G1XYZZ xyzz_dbl_pair(const G1XYZZ& p, bool role, uint32_t pmask) {
-  if (p.is_inf()) return p;
-  Fq U = fp_dbl(p.Y);
-  Fq V, XX, W, S, MM, t1, t2;
-  G1XYZZ r;
-  pair_mul2(U, U, p.X, p.X, role, pmask, V, XX);
-  Fq M = fp_add(fp_dbl(XX), XX);
-  pair_mul2(U, V, p.X, V, role, pmask, W, S);
-  pair_mul2(M, M, V, p.ZZ, role, pmask, MM, r.ZZ);
-  r.X = fp_sub(MM, fp_dbl(S));
-  pair_mul2(M, fp_sub(S, r.X), W, p.Y, role, pmask, t1, t2);
-  r.Y = fp_sub(t1, t2);
-  // both lanes need W * ZZZ; the pair has no second product left to share it with
-  r.ZZZ = fp_mul(W, p.ZZZ);
-  return r;
-}
-
-__device__ __noinline__ void xyzz_add_pair(G1XYZZ& acc, const G1XYZZ& q, bool role, uint32_t pmask) {
-  if (q.is_inf()) return;
-  if (acc.is_inf()) { acc = q; return; }
-  Fq U1, U2, S1, S2;
-  pair_mul2(acc.X, q.ZZ, q.X, acc.ZZ, role, pmask, U1, U2);
-  pair_mul2(acc.Y, q.ZZZ, q.Y, acc.ZZZ, role, pmask, S1, S2);
-  Fq P = fp_sub(U2, U1);
-  Fq Rr = fp_sub(S2, S1);
-  if (P.is_zero()) {
-    if (Rr.is_zero()) acc = xyzz_dbl_pair(acc, role, pmask);
-    else acc = G1XYZZ::inf();
-    return;
-  }
-  Fq ZZ12, ZZZ12, PP, RR, PPP, Qq, t1, t2;
-  pair_mul2(acc.ZZ, q.ZZ, acc.ZZZ, q.ZZZ, role, pmask, ZZ12, ZZZ12);
-  pair_mul2(P, P, Rr, Rr, role, pmask, PP, RR);
-  pair_mul2(P, PP, U1, PP, role, pmask, PPP, Qq);
-  acc.X = fp_sub(fp_sub(RR, PPP), fp_dbl(Qq));
-  pair_mul2(ZZ12, PP, ZZZ12, PPP, role, pmask, acc.ZZ, acc.ZZZ);
-  pair_mul2(Rr, fp_sub(Qq, acc.X), S1, PPP, role, pmask, t1, t2);
-  acc.Y = fp_sub(t1, t2);
-}
-
-__device__ inline G1XYZZ xyzz_mul_small_pair(const G1XYZZ& p, uint32_t k, bool role, uint32_t pmask) {
-  G1XYZZ r = G1XYZZ::inf();
-  int top = 31;
-  while (top >= 0 && !((k >> top) & 1)) top--;
-  for (int i = top; i >= 0; i--) {
-    r = xyzz_dbl_pair(r, role, pmask);
-    if ((k >> i) & 1) xyzz_add_pair(r, p, role, pmask);
-  }
-  return r;
-}
-
 // tree over the 16 pairs of a warp, then over the warps of the CTA; result valid in thread 0 (and 1)
 __device__ inline G1XYZZ block_reduce_xyzz_pair(G1XYZZ v, G1XYZZ* smem /* >= 32 entries */, bool role, uint32_t pmask) {
   for (int o = 16; o > 1; o >>= 1) {
@@ -610,16 +598,18 @@ struct MsmTuning {
   unsigned acc_block;  // CTA size of msm_accumulate
   bool pair;           // lane-pair cooperative reduction in the low-latency schedule
   bool flat;           // flat (equal chunks of entries) accumulation for one-wave launches of that schedule
+  bool tree;           // row / column / bit-plane bucket reduction (msm_reduce.cuh) for K >= 512
 };
 
 static const MsmTuning& msm_tuning() {
   static MsmTuning t = [] {
-    MsmTuning x{0, 65536, 128, true, true};  // measured: a 2^17-point MSM runs 7 % faster with 2 lanes per bucket than with 4
+    MsmTuning x{0, 65536, 128, true, true, true};  // measured: a 2^17-point MSM runs 7 % faster with 2 lanes per bucket than with 4
     if (const char* e = getenv("CAPGPU_RED_SEG")) x.red_seg = atoi(e);
     if (const char* e = getenv("CAPGPU_ACC_THREADS")) x.acc_threads = (size_t)atol(e);
     if (const char* e = getenv("CAPGPU_ACC_BLOCK")) x.acc_block = (unsigned)atoi(e);
     if (const char* e = getenv("CAPGPU_RED_PAIR")) x.pair = atoi(e) != 0;
     if (const char* e = getenv("CAPGPU_ACC_FLAT")) x.flat = atoi(e) != 0;
+    if (const char* e = getenv("CAPGPU_RED_TREE")) x.tree = atoi(e) != 0;
     return x;
   }();
   return t;
@@ -655,33 +645,19 @@ void msm_device(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const F
     CAPGPU_CUDA(cudaMemsetAsync(out_dev, 0, batch * sizeof(G1Affine), ctx->stream));
     return;
   }
-  ctx->msm_digits.reserve(batch * W * n * sizeof(int32_t));
-  ctx->msm_counts.reserve((2 * batch * (K + 2) + batch * K) * sizeof(uint32_t));
+  ctx->msm_digits.reserve(2 * batch * W * n * sizeof(int32_t));
+  ctx->msm_counts.reserve((batch * (K + 2) + 2 * batch * K + batch) * sizeof(uint32_t));
   ctx->msm_entries.reserve(batch * W * n * sizeof(uint32_t));
   ctx->msm_buckets.reserve(batch * K * sizeof(G1XYZZ));
   int32_t* digits = ctx->msm_digits.as<int32_t>();
+  uint32_t* ranks = reinterpret_cast<uint32_t*>(digits + batch * W * n);
   uint32_t* counts = ctx->msm_counts.as<uint32_t>();
-  uint32_t* cursors = counts + batch * (K + 2);
-  uint32_t* order = cursors + batch * (K + 2);
+  uint32_t* order = counts + batch * (K + 2);
+  uint32_t* heavy = order + batch * K;
+  uint32_t* nheavy = heavy + batch * K;
   uint32_t* entries = ctx->msm_entries.as<uint32_t>();
   G1XYZZ* buckets = ctx->msm_buckets.as<G1XYZZ>();
 
-  {
-  ProfScope prof_sort(ctx, PROF_MSM_SORT, (double)batch * W * n);
-  CAPGPU_CUDA(cudaMemsetAsync(counts, 0, batch * (K + 2) * sizeof(uint32_t), ctx->stream));
-  {
-    dim3 grid(ceil_div(n, 128), (unsigned)batch);
-    msm_recode<<<grid, 128, 0, ctx->stream>>>(scalars, n, stride, scalars_mont ? 1 : 0, c, W, digits, counts, K, lo);
-    CAPGPU_LAUNCH_CHECK(ctx);
-  }
-  msm_scan<<<(unsigned)batch, 1024, 0, ctx->stream>>>(counts, cursors, order, K);
-  CAPGPU_LAUNCH_CHECK(ctx);
-  {
-    dim3 grid(ceil_div(n, 256), (unsigned)W, (unsigned)batch);
-    msm_scatter<<<grid, 256, 0, ctx->stream>>>(digits, n, W, cursors, entries, K, srs->n, base_off, lo);
-    CAPGPU_LAUNCH_CHECK(ctx);
-  }
-  }
   // lanes per bucket: aim for ~128k accumulating threads
   size_t lpb = 1;
   // ... but never so many that a lane gets fewer than ~8 additions (the lane tree costs log2(lpb) full adds)
@@ -691,6 +667,32 @@ void msm_device(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const F
   const uint32_t heavy_thr = (uint32_t)(8 * avg_entries > MSM_HEAVY ? 8 * avg_entries : MSM_HEAVY);
   // one-wave launches in the low-latency schedule: equal chunks of sorted entries per thread
   const size_t wave_threads = (size_t)ctx->sm_count * 4 * 128;
+  const size_t ee = es / parts;  // expected entries of this bucket-range slice
+  const bool flat = latency && msm_tuning().flat && batch * K * lpb <= wave_threads && ee >= 4 * wave_threads;
+
+  {
+  ProfScope prof_sort(ctx, PROF_MSM_SORT, (double)batch * W * n);
+  CAPGPU_CUDA(cudaMemsetAsync(counts, 0, batch * (K + 2) * sizeof(uint32_t), ctx->stream));
+  {
+    dim3 grid(ceil_div(n, 128), (unsigned)batch);
+    if (W <= 17) msm_recode<17><<<grid, 128, 0, ctx->stream>>>(scalars, n, stride, scalars_mont ? 1 : 0, c, W, digits, ranks, counts, K, lo);
+    else msm_recode<0><<<grid, 128, 0, ctx->stream>>>(scalars, n, stride, scalars_mont ? 1 : 0, c, W, digits, ranks, counts, K, lo);
+    CAPGPU_LAUNCH_CHECK(ctx);
+  }
+  {
+    static std::once_flag scan_attr[16];
+    std::call_once(scan_attr[ctx->device & 15], [] {
+      cudaFuncSetAttribute(msm_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((((size_t)1 << 15) + 2) * sizeof(uint32_t)));
+    });
+  }
+  msm_scan<<<(unsigned)batch, 1024, (K + 2) * sizeof(uint32_t), ctx->stream>>>(counts, order, heavy, nheavy, K, heavy_thr, flat ? 0 : 1);
+  CAPGPU_LAUNCH_CHECK(ctx);
+  {
+    dim3 grid(ceil_div(n, 256), (unsigned)W, (unsigned)batch);
+    msm_scatter<<<grid, 256, 0, ctx->stream>>>(digits, ranks, n, W, counts, entries, K, srs->n, base_off, lo);
+    CAPGPU_LAUNCH_CHECK(ctx);
+  }
+  }
   // mixed additions of this call = non-zero digits kept by the recode (read back only while profiling:
   // zero witness cells and bucket-range slices make the digit-slot count batch * W * n an overestimate)
   double additions = (double)batch * W * n / parts;
@@ -702,8 +704,9 @@ void msm_device(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const F
     additions = 0;
     for (uint32_t t : totals) additions += t;
   }
-  const size_t ee = es / parts;  // expected entries of this bucket-range slice
-  const bool flat = latency && msm_tuning().flat && batch * K * lpb <= wave_threads && ee >= 4 * wave_threads;
+  // the row / column / bit-plane reduction needs whole rows of 256 buckets
+  const bool tree_reduce = K >= 512 && msm_tuning().tree;
+  FlatParts fl{nullptr, nullptr, nullptr, 0, heavy_thr, 0};
   if (flat) {
     ProfScope prof_acc(ctx, PROF_MSM_ACCUMULATE, additions);
     const size_t per_vec_threads = wave_threads / batch;
@@ -717,13 +720,15 @@ void msm_device(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const F
       msm_accumulate_flat<<<grid, 128, 0, ctx->stream>>>(srs->table, entries, counts, buckets, pfirst, plast, K, es, S, nthreads, heavy_thr);
       CAPGPU_LAUNCH_CHECK(ctx);
     }
-    {
+    if (tree_reduce) {
+      fl = FlatParts{counts, pfirst, plast, S, heavy_thr, nthreads};  // the chunk partials are added up by msm_red_tiles
+    } else {
       dim3 grid(ceil_div(K, 128), (unsigned)batch);
       msm_combine_flat<<<grid, 128, 0, ctx->stream>>>(counts, buckets, pfirst, plast, K, S, nthreads, heavy_thr);
       CAPGPU_LAUNCH_CHECK(ctx);
     }
     dim3 grid((unsigned)(K < 64 ? K : 64), (unsigned)batch);
-    msm_accumulate_heavy<<<grid, 128, 0, ctx->stream>>>(srs->table, entries, counts, order, buckets, K, es, heavy_thr);
+    msm_accumulate_heavy<<<grid, 128, 0, ctx->stream>>>(srs->table, entries, counts, heavy, nheavy, buckets, K, es);
     CAPGPU_LAUNCH_CHECK(ctx);
   } else {
   ProfScope prof_acc(ctx, PROF_MSM_ACCUMULATE, additions);
@@ -737,13 +742,54 @@ void msm_device(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const F
   }
   {
     dim3 grid((unsigned)(K < 64 ? K : 64), (unsigned)batch);
-    msm_accumulate_heavy<<<grid, 128, 0, ctx->stream>>>(srs->table, entries, counts, order, buckets, K, es, heavy_thr);
+    msm_accumulate_heavy<<<grid, 128, 0, ctx->stream>>>(srs->table, entries, counts, heavy, nheavy, buckets, K, es);
     CAPGPU_LAUNCH_CHECK(ctx);
   }
   }
-  // segmented reduction: L buckets per thread.  Depth is ~2L + 36 group operations and work
-  // ~(K/L)(2L + 36), so a lone MSM (latency) wants a small L and a batch (throughput) a large
-  // one: L = 32 by default; in latency mode aim at ~8192 threads per launch, 4 <= L <= 32.
+  ProfScope prof_red(ctx, PROF_MSM_REDUCE, (double)batch * K);
+  if (tree_reduce) {
+    // rows / columns / bit planes (msm_reduce.cuh)
+    const size_t R = K / RED_COLS;
+    const int log_tr = R >= 4 ? 2 : 1;  // tiles of 4 x 8 (2 x 16) buckets
+    const int ncb = RED_COLS >> (5 - log_tr);
+    const size_t nrb = R >> log_tr;
+    const size_t NS = R + RED_COLS;
+    const uint32_t row0 = lo / RED_COLS;
+    int nplanes = 8;
+    for (uint32_t amax = row0 + (uint32_t)R - 1; amax; amax >>= 1) nplanes++;
+    if (nplanes < 9) nplanes = 9;
+    ctx->msm_partials.reserve(batch * (R * ncb + RED_COLS * nrb + NS + 16) * sizeof(G1XYZZ));
+    if (ctx->msm_ticket.bytes < batch * sizeof(uint32_t)) {
+      ctx->msm_ticket.reserve((batch < 64 ? 64 : 2 * batch) * sizeof(uint32_t));
+      CAPGPU_CUDA(cudaMemsetAsync(ctx->msm_ticket.p, 0, ctx->msm_ticket.bytes, ctx->stream));
+    }
+    G1XYZZ* rowpart = ctx->msm_partials.as<G1XYZZ>();
+    G1XYZZ* colpart = rowpart + batch * R * ncb;
+    G1XYZZ* sums = colpart + batch * RED_COLS * nrb;
+    G1XYZZ* planes = sums + batch * NS;
+    {
+      dim3 grid((unsigned)(K / RED_TILE), (unsigned)batch);
+      msm_red_tiles<<<grid, RED_THREADS, 0, ctx->stream>>>(buckets, K, log_tr, rowpart, colpart, fl);
+      CAPGPU_LAUNCH_CHECK(ctx);
+    }
+    {
+      dim3 grid(ceil_div(NS, 2), (unsigned)batch);
+      msm_red_sums<<<grid, RED_THREADS, 0, ctx->stream>>>(rowpart, colpart, R, ncb, (int)nrb, sums);
+      CAPGPU_LAUNCH_CHECK(ctx);
+    }
+    {
+      dim3 grid((unsigned)nplanes, (unsigned)batch);
+      if (batch * nplanes <= (size_t)ctx->sm_count)
+        msm_red_planes<128><<<grid, 512, 0, ctx->stream>>>(sums, R, row0, nplanes, planes, ctx->msm_ticket.as<uint32_t>(), out_dev);
+      else
+        msm_red_planes<32><<<grid, 128, 0, ctx->stream>>>(sums, R, row0, nplanes, planes, ctx->msm_ticket.as<uint32_t>(), out_dev);
+      CAPGPU_LAUNCH_CHECK(ctx);
+    }
+    return;
+  }
+  // few buckets (small windows): segmented running sums.  L buckets per thread; depth is ~2L + 36 group
+  // operations and work ~(K/L)(2L + 36): L = 32 by default; in latency mode aim at ~8192 threads per
+  // launch, 4 <= L <= 32.
   uint32_t L = 32;
   if (latency) {
     L = 4;
@@ -757,7 +803,6 @@ void msm_device(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const F
   unsigned nblocks = ceil_div(T, block);
   ctx->msm_partials.reserve(batch * nblocks * sizeof(G1XYZZ));
   G1XYZZ* partials = ctx->msm_partials.as<G1XYZZ>();
-  ProfScope prof_red(ctx, PROF_MSM_REDUCE, (double)batch * K);
   const bool pair = latency && msm_tuning().pair;  // lane-pair cooperative group operations
   {
     dim3 grid(nblocks, (unsigned)batch);

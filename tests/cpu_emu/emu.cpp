@@ -58,5 +58,7 @@ void emu_g1_mul_small(const uint32_t* pt, uint32_t k, uint32_t* out) {
 extern "C" {
 void emu_fr_inv_fermat(const uint32_t* a, uint32_t* r) { Fr x; memcpy(x.v, a, 32); Fr z = fp_inv_fermat(x); memcpy(r, z.v, 32); }
 void emu_fq_inv_fermat(const uint32_t* a, uint32_t* r) { Fq x; memcpy(x.v, a, 32); Fq z = fp_inv_fermat(x); memcpy(r, z.v, 32); }
+void emu_fr_inv_euclid(const uint32_t* a, uint32_t* r) { Fr x; memcpy(x.v, a, 32); Fr z = fp_inv_euclid(x); memcpy(r, z.v, 32); }
+void emu_fq_inv_euclid(const uint32_t* a, uint32_t* r) { Fq x; memcpy(x.v, a, 32); Fq z = fp_inv_euclid(x); memcpy(r, z.v, 32); }
 }
 
