@@ -104,6 +104,12 @@ __device__ inline G1XYZZ xyzz_mul_small_pair(const G1XYZZ& p, uint32_t k, bool r
 // to WARPSYNC.COLLECTIVE call sequences and cost more than the products they exchange.]
 __device__ __forceinline__ uint32_t quad_role() { return threadIdx.x & 3u; }
 
+// One shared copy of the product / squaring (arguments and result in registers): with the products inlined a
+// quad addition is ~22 KB of straight-line SASS and a lone warp stalls on instruction fetch (ncu:
+// no_instruction 1.6 of 4.7 cycles per issue in msm_red_planes); out of line the loop bodies stay cached.
+static __device__ __noinline__ Fq fq_mul_ool(Fq a, Fq b) { return fp_mul(a, b); }
+static __device__ __noinline__ Fq fq_sqr_ool(Fq a) { return fp_sqr(a); }
+
 __device__ __forceinline__ Fq fq_sel4(uint32_t role, const Fq& a0, const Fq& a1, const Fq& a2, const Fq& a3) {
   Fq r;
   const bool hi = role & 2u, odd = role & 1u;
@@ -132,16 +138,16 @@ __device__ __forceinline__ G1XYZZ xyzz_dbl_quad(const G1XYZZ& p, uint32_t role) 
   Fq U = fp_dbl(p.Y);
   G1XYZZ r;
   // level 1: V = U^2, XX = X^2 (every lane runs the cheaper squaring)
-  Fq m = fp_sqr(fq_sel((role & 1u) != 0, p.X, U));
+  Fq m = fq_sqr_ool(fq_sel((role & 1u) != 0, p.X, U));
   Fq V = fq_quad_get(m, 0), XX = fq_quad_get(m, 1);
   Fq M = fp_add(fp_dbl(XX), XX);
   // level 2: W = U V, S = X V, MM = M^2, ZZ3 = V ZZ
-  m = fp_mul(fq_sel4(role, U, p.X, M, V), fq_sel4(role, V, V, M, p.ZZ));
+  m = fq_mul_ool(fq_sel4(role, U, p.X, M, V), fq_sel4(role, V, V, M, p.ZZ));
   Fq W = fq_quad_get(m, 0), S = fq_quad_get(m, 1), MM = fq_quad_get(m, 2);
   r.ZZ = fq_quad_get(m, 3);
   r.X = fp_sub(MM, fp_dbl(S));
   // level 3: t1 = M (S - X3), t2 = W Y, ZZZ3 = W ZZZ
-  m = fp_mul(fq_sel4(role, M, W, W, W), fq_sel4(role, fp_sub(S, r.X), p.Y, p.ZZZ, p.ZZZ));
+  m = fq_mul_ool(fq_sel4(role, M, W, W, W), fq_sel4(role, fp_sub(S, r.X), p.Y, p.ZZZ, p.ZZZ));
   r.Y = fp_sub(fq_quad_get(m, 0), fq_quad_get(m, 1));
   r.ZZZ = fq_quad_get(m, 2);
   return r;
@@ -151,21 +157,21 @@ __device__ __forceinline__ G1XYZZ xyzz_dbl_quad(const G1XYZZ& p, uint32_t role) 
 __device__ __forceinline__ void xyzz_add_quad(G1XYZZ& acc, const G1XYZZ& b, uint32_t role) {
   const bool a_inf = acc.is_inf(), b_inf = b.is_inf();
   // level 1: U1 = X1 ZZ2, U2 = X2 ZZ1, S1 = Y1 ZZZ2, S2 = Y2 ZZZ1
-  Fq m = fp_mul(fq_sel4(role, acc.X, b.X, acc.Y, b.Y), fq_sel4(role, b.ZZ, acc.ZZ, b.ZZZ, acc.ZZZ));
+  Fq m = fq_mul_ool(fq_sel4(role, acc.X, b.X, acc.Y, b.Y), fq_sel4(role, b.ZZ, acc.ZZ, b.ZZZ, acc.ZZZ));
   Fq U1 = fq_quad_get(m, 0), S1 = fq_quad_get(m, 2);
   Fq P = fp_sub(fq_quad_get(m, 1), U1);
   Fq Rr = fp_sub(fq_quad_get(m, 3), S1);
   // level 2: PP = P^2, RR = R^2, ZZ12 = ZZ1 ZZ2, ZZZ12 = ZZZ1 ZZZ2
-  m = fp_mul(fq_sel4(role, P, Rr, acc.ZZ, acc.ZZZ), fq_sel4(role, P, Rr, b.ZZ, b.ZZZ));
+  m = fq_mul_ool(fq_sel4(role, P, Rr, acc.ZZ, acc.ZZZ), fq_sel4(role, P, Rr, b.ZZ, b.ZZZ));
   Fq PP = fq_quad_get(m, 0), RR = fq_quad_get(m, 1), ZZ12 = fq_quad_get(m, 2), ZZZ12 = fq_quad_get(m, 3);
   // level 3: PPP = P PP, Q = U1 PP, ZZ3 = ZZ12 PP
-  m = fp_mul(fq_sel4(role, P, U1, ZZ12, ZZ12), PP);
+  m = fq_mul_ool(fq_sel4(role, P, U1, ZZ12, ZZ12), PP);
   Fq PPP = fq_quad_get(m, 0), Qq = fq_quad_get(m, 1);
   G1XYZZ r;
   r.ZZ = fq_quad_get(m, 2);
   r.X = fp_sub(fp_sub(RR, PPP), fp_dbl(Qq));
   // level 4: t1 = R (Q - X3), t2 = S1 PPP, ZZZ3 = ZZZ12 PPP
-  m = fp_mul(fq_sel4(role, Rr, S1, ZZZ12, ZZZ12), fq_sel4(role, fp_sub(Qq, r.X), PPP, PPP, PPP));
+  m = fq_mul_ool(fq_sel4(role, Rr, S1, ZZZ12, ZZZ12), fq_sel4(role, fp_sub(Qq, r.X), PPP, PPP, PPP));
   r.Y = fp_sub(fq_quad_get(m, 0), fq_quad_get(m, 1));
   r.ZZZ = fq_quad_get(m, 2);
   // special cases: equal x-coordinates (P = 0) with both operands finite

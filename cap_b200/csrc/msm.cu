@@ -577,21 +577,6 @@ __global__ void msm_finalize(const G1XYZZ* partials, uint32_t nparts, G1Affine* 
 // ------------------------------------------------------------------------------------------
 static int ceil_log2(size_t x) { int l = 0; while (((size_t)1 << l) < x) l++; return l; }
 
-// Window size c (2^(c-1) buckets, W = ceil(255 / c) window-shifted tables).  Bucket accumulation costs
-// n W mixed additions, the bucket reduction ~2.8 full additions per bucket at half the lane efficiency.
-// Measured on one lockstep group of 8 proofs at n = 2^15 (profiles/r2_launches_group8.csv): with c = 16
-// the reduction took 0.53 of the accumulation time; c = floor(log2 n) balances the two (c = 15 at
-// n = 2^15: 6 % more additions, half the buckets).  A lone MSM of 2^12..2^14 points is latency-bound
-// (bucket chains, then the reduction) and prefers many short buckets: c >= 15 there.
-static int choose_window(size_t n_points) {
-  int c = ceil_log2(n_points + 1) - 1;  // floor(log2 n)
-  if (c > 16) c = 16;
-  if (c < 4) c = 4;
-  if (n_points >= ((size_t)1 << 12) && c < 15) c = 15;
-  if (const char* e = getenv("CAPGPU_WINDOW_BITS")) { int v = atoi(e); if (v >= 2 && v <= 16) c = v; }  // A/B runs only
-  return c;
-}
-
 struct MsmTuning {
   int red_seg;         // buckets per thread in the segmented reduction (0 = heuristic)
   size_t acc_threads;  // target thread count when choosing lanes per bucket
@@ -599,21 +584,44 @@ struct MsmTuning {
   bool pair;           // lane-pair cooperative reduction in the low-latency schedule
   bool flat;           // flat (equal chunks of entries) accumulation for one-wave launches of that schedule
   bool tree;           // row / column / bit-plane bucket reduction (msm_reduce.cuh) for K >= 512
+  size_t strip_min;    // buckets per launch from which the single-lane strip form of its first stage is used
+  uint32_t flat_smin;  // fewest entries per thread of the flat accumulation
+  int window_min;      // smallest automatic window for n >= 2^12
 };
 
 static const MsmTuning& msm_tuning() {
   static MsmTuning t = [] {
-    MsmTuning x{0, 65536, 128, true, true, true};  // measured: a 2^17-point MSM runs 7 % faster with 2 lanes per bucket than with 4
+    MsmTuning x{0, 65536, 128, true, true, true, (size_t)1 << 17, 8, 15};  // measured: a 2^17-point MSM runs 7 % faster with 2 lanes per bucket than with 4
     if (const char* e = getenv("CAPGPU_RED_SEG")) x.red_seg = atoi(e);
     if (const char* e = getenv("CAPGPU_ACC_THREADS")) x.acc_threads = (size_t)atol(e);
     if (const char* e = getenv("CAPGPU_ACC_BLOCK")) x.acc_block = (unsigned)atoi(e);
     if (const char* e = getenv("CAPGPU_RED_PAIR")) x.pair = atoi(e) != 0;
     if (const char* e = getenv("CAPGPU_ACC_FLAT")) x.flat = atoi(e) != 0;
     if (const char* e = getenv("CAPGPU_RED_TREE")) x.tree = atoi(e) != 0;
+    if (const char* e = getenv("CAPGPU_RED_STRIP_MIN")) x.strip_min = (size_t)atol(e);
+    if (const char* e = getenv("CAPGPU_FLAT_SMIN")) x.flat_smin = (uint32_t)atoi(e);
+    if (const char* e = getenv("CAPGPU_WINDOW_MIN")) x.window_min = atoi(e);
     return x;
   }();
   return t;
 }
+
+// Window size c (2^(c-1) buckets, W = ceil(255 / c) window-shifted tables).  Bucket accumulation costs
+// n W mixed additions, the bucket reduction ~2.8 full additions per bucket at half the lane efficiency.
+// Measured on one lockstep group of 8 proofs at n = 2^15 (profiles/r2_launches_group8.csv): with c = 16
+// the reduction took 0.53 of the accumulation time; c = floor(log2 n) balances the two (c = 15 at
+// n = 2^15: 6 % more additions, half the buckets).  A lone MSM of 2^12..2^14 points keeps c = 15: smaller
+// windows leave only 254 mod c bits for the top window (c = 13: 7, c = 14: 2), whose few buckets then
+// collect n / 2^7 .. n / 4 entries each (measured: 2^14 points at c = 14 take 0.59 ms, 0.28 ms at c = 15).
+static int choose_window(size_t n_points) {
+  int c = ceil_log2(n_points + 1) - 1;  // floor(log2 n)
+  if (c > 16) c = 16;
+  if (c < 4) c = 4;
+  if (n_points >= ((size_t)1 << 12) && c < msm_tuning().window_min) c = msm_tuning().window_min;
+  if (const char* e = getenv("CAPGPU_WINDOW_BITS")) { int v = atoi(e); if (v >= 2 && v <= 16) c = v; }  // A/B runs only
+  return c;
+}
+
 
 template <int LPB, int MINB>
 static void launch_accumulate2(capgpu_ctx* ctx, const capgpu_srs* srs, size_t K, const uint32_t* entries, const uint32_t* offsets,
@@ -710,7 +718,8 @@ void msm_device(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const F
   if (flat) {
     ProfScope prof_acc(ctx, PROF_MSM_ACCUMULATE, additions);
     const size_t per_vec_threads = wave_threads / batch;
-    const uint32_t S = (uint32_t)((ee + per_vec_threads - 1) / per_vec_threads);
+    uint32_t S = (uint32_t)((ee + per_vec_threads - 1) / per_vec_threads);
+    if (S < msm_tuning().flat_smin) S = msm_tuning().flat_smin;
     const size_t nthreads = (es + S - 1) / S;  // covers the worst case (every digit in this slice); idle threads exit at once
     ctx->msm_flat.reserve(2 * batch * nthreads * sizeof(G1XYZZ));
     G1XYZZ* pfirst = ctx->msm_flat.as<G1XYZZ>();
@@ -750,9 +759,13 @@ void msm_device(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const F
   if (tree_reduce) {
     // rows / columns / bit planes (msm_reduce.cuh)
     const size_t R = K / RED_COLS;
-    const int log_tr = R >= 4 ? 2 : 1;  // tiles of 4 x 8 (2 x 16) buckets
-    const int ncb = RED_COLS >> (5 - log_tr);
-    const size_t nrb = R >> log_tr;
+    // lone MSMs / small batches: lane-quad tiles of 4 x 8 (2 x 16) buckets (shortest chain); many vectors per
+    // launch: single-lane strips of 16 buckets (least multiply-pipe time)
+    const bool strips = !flat && batch * K >= msm_tuning().strip_min && R >= 2;
+    const int log_tr = R >= 4 ? 2 : 1;
+    const int log_sl = R >= 16 ? 4 : (R >= 8 ? 3 : (R >= 4 ? 2 : 1));
+    const int ncb = strips ? 16 : RED_COLS >> (5 - log_tr);
+    const size_t nrb = strips ? R >> log_sl : R >> log_tr;
     const size_t NS = R + RED_COLS;
     const uint32_t row0 = lo / RED_COLS;
     int nplanes = 8;
@@ -767,12 +780,20 @@ void msm_device(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const F
     G1XYZZ* colpart = rowpart + batch * R * ncb;
     G1XYZZ* sums = colpart + batch * RED_COLS * nrb;
     G1XYZZ* planes = sums + batch * NS;
-    {
+    if (strips) {
+      dim3 grid(ceil_div(K / 16 + RED_COLS * nrb, 128), (unsigned)batch);
+      msm_red_strips<<<grid, 128, 0, ctx->stream>>>(buckets, K, log_sl, rowpart, colpart);
+      CAPGPU_LAUNCH_CHECK(ctx);
+    } else {
       dim3 grid((unsigned)(K / RED_TILE), (unsigned)batch);
       msm_red_tiles<<<grid, RED_THREADS, 0, ctx->stream>>>(buckets, K, log_tr, rowpart, colpart, fl);
       CAPGPU_LAUNCH_CHECK(ctx);
     }
-    {
+    if (strips) {
+      dim3 grid(ceil_div(NS, 128), (unsigned)batch);
+      msm_red_sums_lane<<<grid, 128, 0, ctx->stream>>>(rowpart, colpart, R, ncb, (int)nrb, sums);
+      CAPGPU_LAUNCH_CHECK(ctx);
+    } else {
       dim3 grid(ceil_div(NS, 2), (unsigned)batch);
       msm_red_sums<<<grid, RED_THREADS, 0, ctx->stream>>>(rowpart, colpart, R, ncb, (int)nrb, sums);
       CAPGPU_LAUNCH_CHECK(ctx);

@@ -135,6 +135,40 @@ __global__ void __launch_bounds__(RED_THREADS, 4) msm_red_tiles(const G1XYZZ* __
   }
 }
 
+// Throughput form of msm_red_tiles (many vectors per launch, nothing waits for one result): one THREAD per strip
+// of 16 buckets, plain single-lane additions (ec.cuh) with every lane of every warp busy - 0.66 of the
+// multiply-pipe time of the quad form per addition, at 16 sequential additions of latency.  Threads
+// 0 .. K/16 - 1 sum the row strips (a, 16 j .. 16 j + 15) -> rowpart[a][j]; threads K/16 .. 2 K/16 - 1 the
+// column strips (SL i .. SL i + SL - 1, c), SL = min(16, R) -> colpart[c][i].
+__global__ void __launch_bounds__(128, 4) msm_red_strips(const G1XYZZ* __restrict__ buckets, size_t K, int log_sl, G1XYZZ* rowpart,
+                                                         G1XYZZ* colpart) {
+  const size_t b = blockIdx.y;
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t R = K / RED_COLS;
+  const size_t nrow = K / 16, ncol = (size_t)RED_COLS * (R >> log_sl);
+  const G1XYZZ* bk = buckets + b * K;
+  if (t < nrow) {
+    const G1XYZZ* src = bk + t * 16;  // strip j = t % 16 of row a = t / 16
+    G1XYZZ acc = src[0];
+    for (int i = 1; i < 16; i++) {
+      G1XYZZ q = src[i];
+      xyzz_add(acc, q);
+    }
+    rowpart[b * nrow + t] = acc;  // [a][j], 16 strips per row
+  } else if (t < nrow + ncol) {
+    const size_t u = t - nrow;
+    const size_t c = u % RED_COLS, i = u / RED_COLS;  // adjacent threads read adjacent buckets
+    const size_t SL = (size_t)1 << log_sl;
+    const G1XYZZ* src = bk + (i * SL) * RED_COLS + c;
+    G1XYZZ acc = src[0];
+    for (size_t r = 1; r < SL; r++) {
+      G1XYZZ q = src[r * RED_COLS];
+      xyzz_add(acc, q);
+    }
+    colpart[(b * RED_COLS + c) * (R >> log_sl) + i] = acc;
+  }
+}
+
 // sums[b][s], s < R: A_s = sum of rowpart[b][s][0 .. ncb);  s >= R: C_(s - R) = sum of colpart[b][s - R][0 .. nrb)
 // (ncb, nrb <= 32).  Two sums per CTA, 16 quads per sum.
 __global__ void __launch_bounds__(RED_THREADS, 4) msm_red_sums(const G1XYZZ* __restrict__ rowpart, const G1XYZZ* __restrict__ colpart,
@@ -172,6 +206,24 @@ __global__ void __launch_bounds__(RED_THREADS, 4) msm_red_sums(const G1XYZZ* __r
     G1XYZZ x = T[g];
     st_xyzz_quad(sums + b * NS + s, x, role);
   }
+}
+
+// Throughput form of msm_red_sums: one thread per sum, sequential single-lane additions (<= 15 per row sum,
+// <= 7 per column sum after msm_red_strips) instead of a 16-quad tree per sum.
+__global__ void __launch_bounds__(128, 4) msm_red_sums_lane(const G1XYZZ* __restrict__ rowpart, const G1XYZZ* __restrict__ colpart,
+                                                            size_t R, int ncb, int nrb, G1XYZZ* sums) {
+  const size_t b = blockIdx.y;
+  const size_t NS = R + RED_COLS;
+  const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= NS) return;
+  const G1XYZZ* items = s < R ? rowpart + (b * R + s) * ncb : colpart + (b * RED_COLS + (s - R)) * nrb;
+  const int cnt = s < R ? ncb : nrb;
+  G1XYZZ acc = items[0];
+  for (int i = 1; i < cnt; i++) {
+    G1XYZZ q = items[i];
+    xyzz_add(acc, q);
+  }
+  sums[b * NS + s] = acc;
 }
 
 // Plane p (blockIdx.x) of vector b (blockIdx.y): Z_p, then 2^p * Z_p -> planes[b][p]; the last CTA of a vector
