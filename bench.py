@@ -85,7 +85,8 @@ def build_workload(name: str, witness: str = "dense", witnesses: int = N_WITNESS
 
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
-    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap,utilization.gpu,power.draw")
 
     def __init__(self, index: int):
         self.index = index
@@ -107,7 +108,7 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.proc.kill()
             out, _ = self.proc.communicate()
-        sm, mx, reasons = [], [], set()
+        sm, mx, reasons, util, power = [], [], set(), [], []
         for line in out.splitlines():
             f = [x.strip() for x in line.split(",")]
             if len(f) < 6:
@@ -117,11 +118,17 @@ class ClockSampler:
                 mx.append(float(f[1]))
             except ValueError:
                 continue
+            try:  # steady-state evidence: share of the sampling periods with a kernel resident, board power
+                util.append(float(f[6]))
+                power.append(float(f[7]))
+            except (ValueError, IndexError):
+                pass
             for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm),
+                "gpu_util_pct": statistics.median(util) if util else None, "power_w": statistics.median(power) if power else None}
 
 
 # --------------------------------------------------------------------------------------------
