@@ -22,6 +22,7 @@ EXPORTS = [
     "capgpu_calibrate", "capgpu_prove_dev", "capgpu_profile_enable", "capgpu_profile_read", "capgpu_ctx_set_latency_mode", "capgpu_g1_sum_dev", "capgpu_srs_upload_compressed", "capgpu_prove_batch",
     "capgpu_ctx_set_group", "capgpu_pk_info", "capgpu_prove_batch_dev", "capgpu_queue_create", "capgpu_queue_destroy", "capgpu_submit", "capgpu_poll", "capgpu_wait", "capgpu_queue_stats",
     "capgpu_sha256", "capgpu_srs_load_serialized", "capgpu_pk_load_serialized", "capgpu_proof_serialize", "capgpu_fr_rand_from_words", "capgpu_msm_g1_dev_part",
+    "capgpu_curve_msm_g1", "capgpu_curve_fq_op",
 ]
 
 
@@ -118,6 +119,8 @@ def load() -> ctypes.CDLL:
         "capgpu_debug_read": (c_int, [c_void_p, c_int, c_void_p, c_size_t, POINTER(c_size_t)]),
         "capgpu_launch_count": (c_uint64, [c_void_p]),
         "capgpu_calibrate": (c_int, [c_void_p, POINTER(c_double), POINTER(c_double), POINTER(c_double)]),
+        "capgpu_curve_msm_g1": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+        "capgpu_curve_fq_op": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(lib, name, None)

@@ -14,7 +14,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libcapgpu.so")
-SOURCES = ["capi.cu", "ntt.cu", "msm.cu", "poly.cu", "prover.cu", "formats.cu"]
+SOURCES = ["capi.cu", "ntt.cu", "msm.cu", "poly.cu", "prover.cu", "formats.cu", "msm_curve.cu"]
 HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))) + [os.path.join("..", "..", "include", "capgpu.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",

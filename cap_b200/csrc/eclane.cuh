@@ -186,4 +186,15 @@ __device__ __forceinline__ void xyzz_add_quad(G1XYZZ& acc, const G1XYZZ& b, uint
   acc = xyzz_sel(b_inf, acc, r);
 }
 
+
+// One shared out-of-line copy of the quad addition for the reduction kernels (operands and result through
+// memory: shared, global or local): every call site of a kernel then runs the same ~600 cached instructions
+// instead of its own inlined copy - a lone warp walking cold straight-line code waits on instruction fetch.
+// *acc += *b; lane `role` of the quad stores coordinate `role` of the sum to dst when `store` is set.
+static __device__ __noinline__ void xyzz_add_quad_mem(const G1XYZZ* acc, const G1XYZZ* b, G1XYZZ* dst, bool store, uint32_t role) {
+  G1XYZZ x = *acc, y = *b;
+  xyzz_add_quad(x, y, role);
+  if (store) reinterpret_cast<Fq*>(dst)[role] = fq_sel4(role, x.X, x.Y, x.ZZ, x.ZZZ);
+}
+
 }  // namespace capgpu

@@ -41,6 +41,8 @@ struct FlatParts {
   size_t nthreads;
 };
 
+__device__ G1XYZZ g_xyzz_inf;  // zero-initialised: the point at infinity, operand of idle quads
+
 __device__ __forceinline__ G1XYZZ ldcg_xyzz(const G1XYZZ* p) {
   G1XYZZ r;
   const uint4* s = reinterpret_cast<const uint4*>(p);
@@ -90,12 +92,13 @@ __global__ void __launch_bounds__(RED_THREADS, 4) msm_red_tiles(const G1XYZZ* __
         }
       }
     }
-    for (uint32_t i = 0; __any_sync(0xffffffffu, i < extra); i++) {
-      G1XYZZ o = G1XYZZ::inf();
-      if (i < extra) o = next[i];
-      xyzz_add_quad(v, o, role);
-    }
     st_xyzz_quad(&V[g], v, role);
+    __syncwarp();
+    for (uint32_t i = 0; __any_sync(0xffffffffu, i < extra); i++) {
+      const bool on = i < extra;
+      xyzz_add_quad_mem(&V[g], on ? next + i : &g_xyzz_inf, &V[g], on, role);
+      __syncwarp();
+    }
   }
   __syncthreads();
   const int levels = log_tc > log_tr ? log_tc : log_tr;
@@ -104,7 +107,7 @@ __global__ void __launch_bounds__(RED_THREADS, 4) msm_red_tiles(const G1XYZZ* __
     const int nrow = l <= log_tc ? (TR << lwc) : 0;
     const int ncol = l <= log_tr ? (TC << lwr) : 0;
     if (g0 < nrow + ncol) {  // uniform per warp
-      const G1XYZZ *px = nullptr, *py = nullptr;
+      const G1XYZZ *px = &g_xyzz_inf, *py = &g_xyzz_inf;
       G1XYZZ* pd = nullptr;
       if (g < nrow) {
         const int r = g >> lwc, j = g & ((1 << lwc) - 1), wc = 1 << lwc;
@@ -117,10 +120,7 @@ __global__ void __launch_bounds__(RED_THREADS, 4) msm_red_tiles(const G1XYZZ* __
         else { px = &CS[c * (TR / 2) + j]; py = px + wr; }
         pd = &CS[c * (TR / 2) + j];
       }
-      G1XYZZ x = G1XYZZ::inf(), y = G1XYZZ::inf();
-      if (pd) { x = *px; y = *py; }
-      xyzz_add_quad(x, y, role);
-      if (pd) st_xyzz_quad(pd, x, role);
+      xyzz_add_quad_mem(px, py, pd, pd != nullptr, role);
     }
     __syncthreads();
   }
@@ -182,23 +182,20 @@ __global__ void __launch_bounds__(RED_THREADS, 4) msm_red_sums(const G1XYZZ* __r
   const size_t s = (size_t)blockIdx.x * 2 + (g >> 4);
   const int j = g & 15;
   {
-    G1XYZZ x = G1XYZZ::inf(), y = G1XYZZ::inf();
+    const G1XYZZ *px = &g_xyzz_inf, *py = &g_xyzz_inf;
     if (s < NS) {
       const G1XYZZ* items = s < R ? rowpart + (b * R + s) * ncb : colpart + (b * RED_COLS + (s - R)) * nrb;
       const int cnt = s < R ? ncb : nrb;
-      if (j < cnt) x = items[j];
-      if (j + 16 < cnt) y = items[j + 16];
+      if (j < cnt) px = items + j;
+      if (j + 16 < cnt) py = items + j + 16;
     }
-    xyzz_add_quad(x, y, role);
-    st_xyzz_quad(&T[g], x, role);
+    xyzz_add_quad_mem(px, py, &T[g], true, role);
   }
   __syncthreads();
   for (int w = 8; w >= 1; w >>= 1) {
     if (j0 < w) {  // uniform per warp
-      G1XYZZ x = G1XYZZ::inf(), y = G1XYZZ::inf();
-      if (j < w) { x = T[g]; y = T[g + w]; }
-      xyzz_add_quad(x, y, role);
-      if (j < w) st_xyzz_quad(&T[g], x, role);
+      const bool on = j < w;
+      xyzz_add_quad_mem(on ? &T[g] : &g_xyzz_inf, on ? &T[g + w] : &g_xyzz_inf, &T[g], on, role);
     }
     __syncthreads();
   }
@@ -247,37 +244,32 @@ __global__ void __launch_bounds__(4 * QUADS, (QUADS <= 32 ? 4 : 1)) msm_red_plan
     // terms of Z_p: the i-th c with bit p of (c + 1) set (128 of them for p < 8, c = 255 alone for p = 8), and
     // row i when bit (p - 8) of a' = row0 + i is set; quad g takes the terms i = g, g + QUADS, ..  A column and a
     // row term meet only at (p = 8, i = 0): that row term is added after the loop.
-    auto term = [&](int i) {
-      G1XYZZ y = G1XYZZ::inf();
+    auto term = [&](int i) -> const G1XYZZ* {
       if (p < 8) {
         const uint32_t v = (((uint32_t)i >> p) << (p + 1)) | (1u << p) | ((uint32_t)i & ((1u << p) - 1u));
-        y = C[v - 1];
-      } else if (p == 8 && i == 0) {
-        y = C[255];
-      } else if (p >= 8 && (size_t)i < R && (((row0 + (uint32_t)i) >> (p - 8)) & 1u)) {
-        y = A[i];
+        return C + (v - 1);
       }
-      return y;
+      if (p == 8 && i == 0) return C + 255;
+      if ((size_t)i < R && (((row0 + (uint32_t)i) >> (p - 8)) & 1u)) return A + i;
+      return &g_xyzz_inf;
     };
-    G1XYZZ x = term(g);
+    const G1XYZZ* px = term(g);
+    G1XYZZ x = *px;
+    st_xyzz_quad(&T[g], x, role);
+    __syncwarp();
     for (int it = 1; it < 128 / QUADS; it++) {  // uniform trip count
-      G1XYZZ y = term(g + it * QUADS);
-      xyzz_add_quad(x, y, role);
+      xyzz_add_quad_mem(&T[g], term(g + it * QUADS), &T[g], true, role);
+      __syncwarp();
     }
     if (p == 8) {  // uniform per CTA
-      G1XYZZ y = G1XYZZ::inf();
-      if (g == 0 && (row0 & 1u)) y = A[0];
-      xyzz_add_quad(x, y, role);
+      xyzz_add_quad_mem(&T[g], (g == 0 && (row0 & 1u)) ? A : &g_xyzz_inf, &T[g], true, role);
     }
-    st_xyzz_quad(&T[g], x, role);
   }
   __syncthreads();
   for (int w = QUADS / 2; w >= 1; w >>= 1) {
     if (g0 < w) {  // uniform per warp
-      G1XYZZ x = G1XYZZ::inf(), y = G1XYZZ::inf();
-      if (g < w) { x = T[g]; y = T[g + w]; }
-      xyzz_add_quad(x, y, role);
-      if (g < w) st_xyzz_quad(&T[g], x, role);
+      const bool on = g < w;
+      xyzz_add_quad_mem(on ? &T[g] : &g_xyzz_inf, on ? &T[g + w] : &g_xyzz_inf, &T[g], on, role);
     }
     __syncthreads();
   }
@@ -299,10 +291,8 @@ __global__ void __launch_bounds__(4 * QUADS, (QUADS <= 32 ? 4 : 1)) msm_red_plan
   __syncthreads();
   for (int w = 8; w >= 1; w >>= 1) {
     if (g0 < w) {
-      G1XYZZ x = G1XYZZ::inf(), y = G1XYZZ::inf();
-      if (g < w) { x = T[g]; y = T[g + w]; }
-      xyzz_add_quad(x, y, role);
-      if (g < w) st_xyzz_quad(&T[g], x, role);
+      const bool on = g < w;
+      xyzz_add_quad_mem(on ? &T[g] : &g_xyzz_inf, on ? &T[g + w] : &g_xyzz_inf, &T[g], on, role);
     }
     __syncthreads();
   }

@@ -308,6 +308,24 @@ int capgpu_profile_read(const capgpu_ctx* ctx, int id, double* total_ms, uint64_
  * plain IMAD and for IMAD.WIDE.U32, and the Montgomery multiplication rate (G mul/s). */
 int capgpu_calibrate(capgpu_ctx* ctx, double* gimad_per_s, double* gimad_wide_per_s, double* gfmul_per_s);
 
+/* ---- the other pairing curves of the reference (src/config.rs:86-114) ---------------------------------
+ * CAP is generic over `CapConfig::PairingCurve`; besides the default BN254 the reference builds with the
+ * cargo features `bls12_381` / `bls12_377` (Cargo.toml:71-75), whose G1 lives over 381- / 377-bit base
+ * fields (ark-ff `Fp384`: 6 x u64 limbs, Montgomery with R = 2^384).  These two entry points replace
+ * `VariableBaseMSM::multi_scalar_mul` on `GroupAffine<ark_bls12_381::g1::Parameters>` /
+ * `<ark_bls12_377::g1::Parameters>` and the `Fp384` arithmetic under it.  The prover entry points above are
+ * BN254 only.
+ *   points_xy : n x 12 u64, x[6] || y[6] little-endian Montgomery limbs, all-zero = infinity
+ *   scalars   : n x 4 u64 canonical (`into_repr`) scalars of the curve's Fr (255 / 253 bits)
+ *   out_xy    : 12 u64, affine result in the same layout
+ * capgpu_curve_fq_op: element-wise base-field operation on `count` elements (6 u64 each, Montgomery):
+ *   op 0 a*b, 1 a^2, 2 a^-1 (batched binary GCD), 3 a+b, 4 a-b, 5 a^-1 by Fermat (cross-check); b may be
+ *   NULL for the unary ones. */
+#define CAPGPU_CURVE_BLS12_381 1
+#define CAPGPU_CURVE_BLS12_377 2
+int capgpu_curve_msm_g1(capgpu_ctx* ctx, int curve, const uint64_t* points_xy, const uint64_t* scalars, size_t n, uint64_t* out_xy);
+int capgpu_curve_fq_op(capgpu_ctx* ctx, int curve, int op, const uint64_t* a, const uint64_t* b, uint64_t* out, size_t count);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,7 +40,7 @@ def _build_emu(name: str) -> ctypes.CDLL:
     outdir = os.path.join(ROOT, "tests", "cpu_emu", "build")
     os.makedirs(outdir, exist_ok=True)
     so = os.path.join(outdir, name + ".so")
-    deps = [src] + [os.path.join(ROOT, "cap_b200", "csrc", f) for f in ("fp.cuh", "ec.cuh", "hostfp.h", "transcript.h")]
+    deps = [src] + [os.path.join(ROOT, "cap_b200", "csrc", f) for f in ("fp.cuh", "ec.cuh", "fpn.cuh", "hostfp.h", "transcript.h")]
     if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
         subprocess.run(["g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-o", so, src], check=True)
     return ctypes.CDLL(so)

@@ -62,3 +62,42 @@ void emu_fr_inv_euclid(const uint32_t* a, uint32_t* r) { Fr x; memcpy(x.v, a, 32
 void emu_fq_inv_euclid(const uint32_t* a, uint32_t* r) { Fq x; memcpy(x.v, a, 32); Fq z = fp_inv_euclid(x); memcpy(r, z.v, 32); }
 }
 
+
+// ---- 12-limb fields / G1 of BLS12-381 (curve 1) and BLS12-377 (curve 2): fpn.cuh -----------------------
+#include "../../cap_b200/csrc/fpn.cuh"
+template <class F>
+static void fqn_op(int op, const uint32_t* a, const uint32_t* b, uint32_t* r) {
+  F x, y, z;
+  memcpy(x.v, a, sizeof x.v);
+  if (b) memcpy(y.v, b, sizeof y.v); else y = F::zero();
+  switch (op) {
+    case 0: z = fp_mul(x, y); break;
+    case 1: z = fp_sqr(x); break;
+    case 2: z = fp_inv(x); break;
+    case 3: z = fp_add(x, y); break;
+    case 4: z = fp_sub(x, y); break;
+    case 5: z = fp_inv_fermat(x); break;
+    case 6: z = fp_neg(x); break;
+    default: z = fp_from_mont(x); break;
+  }
+  memcpy(r, z.v, sizeof z.v);
+}
+// sum of +-points by mixed additions, then + (sum of a second list) by a full addition, doubled `dbl` times, to affine
+template <class F>
+static void g1n_chain(const uint32_t* pts_a, const int* negs, int na, const uint32_t* pts_b, int nb, int dbl, uint32_t* out) {
+  G1XyzzT<F> a = G1XyzzT<F>::inf(), b = G1XyzzT<F>::inf();
+  for (int i = 0; i < na; i++) { G1AffineT<F> p; memcpy(&p, pts_a + 2 * F::N * i, sizeof p); if (!p.is_inf()) xyzz_add_mixed(a, p.x, p.y, negs[i] != 0); }
+  for (int i = 0; i < nb; i++) { G1AffineT<F> p; memcpy(&p, pts_b + 2 * F::N * i, sizeof p); if (!p.is_inf()) xyzz_add_mixed(b, p.x, p.y, false); }
+  xyzz_add(a, b);
+  for (int i = 0; i < dbl; i++) a = xyzz_dbl(a);
+  G1AffineT<F> r = xyzz_to_affine(a);
+  memcpy(out, &r, sizeof r);
+}
+extern "C" {
+void emu_fqn_op(int curve, int op, const uint32_t* a, const uint32_t* b, uint32_t* r) {
+  if (curve == 1) fqn_op<Fq381>(op, a, b, r); else fqn_op<Fq377>(op, a, b, r);
+}
+void emu_g1n_chain(int curve, const uint32_t* pts_a, const int* negs, int na, const uint32_t* pts_b, int nb, int dbl, uint32_t* out) {
+  if (curve == 1) g1n_chain<Fq381>(pts_a, negs, na, pts_b, nb, dbl, out); else g1n_chain<Fq377>(pts_a, negs, na, pts_b, nb, dbl, out);
+}
+}
