@@ -51,9 +51,9 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="capgpu", choices=["capgpu", "reference"])
     ap.add_argument("--workload", default="transfer_2x2")
-    ap.add_argument("--batch", type=int, default=64, help="independent notes per GPU per step")
+    ap.add_argument("--batch", type=int, default=256, help="independent notes per GPU per step")
     ap.add_argument("--ctxs", type=int, default=int(os.environ.get("BENCH_CTXS", "4")), help="prover contexts (host thread + CUDA stream) per GPU")
-    ap.add_argument("--group", type=int, default=8, help="notes a context proves in lockstep (capgpu_ctx_set_group)")
+    ap.add_argument("--group", type=int, default=16, help="notes a context proves in lockstep (capgpu_ctx_set_group)")
     ap.add_argument("--cpu-sample", type=int, default=-1, help="proofs in the cpu_baseline sample (-1: one per host thread, 0 disables)")
     ap.add_argument("--witness", default="dense", choices=["dense", "sparse"],
                     help="dense: uniform witness (the headline workload); sparse: 45%% of gate inputs unused (zero variable), "
@@ -380,7 +380,7 @@ def side_measurements(args, torch, ctxs, pk, srs, circ, wires_dev, wires, pubs, 
         prof[name] = {"ms_per_proof": ms.value / reps, "launches_per_proof": cnt.value / reps, "units_per_proof": units.value / reps}
     _lib.check(lib.capgpu_profile_enable(ctx.h, 0), ctx.h)
     acc = prof["msm_accumulate"]
-    launches = max(acc["launches_per_proof"], 1)
+    launches = acc["launches_per_proof"] or 1.0  # a lockstep group of G proofs shares 4 launches: 4 / G per proof
     madds_per_launch = acc["units_per_proof"] / launches
     wide_mads = madds_per_launch * MADD_F_MULS * F_MUL_WIDE_MADS
     sec_per_launch = acc["ms_per_proof"] / launches * 1e-3
@@ -389,10 +389,12 @@ def side_measurements(args, torch, ctxs, pk, srs, circ, wires_dev, wires, pubs, 
         "kernel": "msm_accumulate (Pippenger bucket accumulation, XYZZ mixed adds)",
         "bound": "imad", "achieved": achieved, "peak": imad_peak, "unit": "G IMAD.WIDE lane-ops/s",
         "frac": achieved / imad_peak if imad_peak else None,
-        # dram__bytes_read.sum + dram__bytes_write.sum of the batch-of-5 launch (2.62 M additions) in the
-        # committed capture profiles/r1_ncu_full_final_raw.csv; algorithmic gather traffic of that launch is
-        # 2.62 M x 68 B = 178 MB, served mostly from L2 (the 33 MB window-shifted table is L2 resident)
-        "traffic": 46.55e6, "traffic_source": "profiles/r1_ncu_full_final_raw.csv (ncu --set full, batch-of-5 launch: 42.8 MB read + 3.7 MB written; the 33 MB window table stays in L2, the 178 MB of algorithmic gathers mostly hit it)",
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the four accumulate launches of a
+        # lockstep group of 8 proofs (batches of 40 / 8 / 40 / 16 scalar vectors) in the committed capture
+        # profiles/r2_ncu_accumulate_group8_raw.csv: (267 + 62 + 291 + 108) MB / 4.  Algorithmic gather traffic of
+        # those launches is 14.1 M additions x 68 B = 962 MB on average, served mostly from L2 (the 36 MB
+        # window-shifted table is L2 resident)
+        "traffic": 182e6, "traffic_source": "profiles/r2_ncu_accumulate_group8_raw.csv (ncu --set full, the 4 accumulate launches of a lockstep group of 8: 728 MB read + written in total; the 36 MB window table stays in L2, the 3.8 GB of algorithmic gathers mostly hit it; sm__pipe_fmaheavy_cycles_active 85-90 % of elapsed)",
         "peak_source": "measured in this run by capgpu_calibrate (integer multiply-add issue rate; MEASURED_PEAKS.json has no INT32 figure)",
         "fmul_microbench_gmul_per_s": calib["gfmul_per_s"],
         "frac_of_fmul_microbench": (madds_per_launch * MADD_F_MULS / sec_per_launch * 1e-9 / calib["gfmul_per_s"]) if sec_per_launch > 0 else None,
@@ -500,7 +502,7 @@ def other_configs(args, torch, ctxs, calib, imad_peak):
 
     # -- note shapes ---------------------------------------------------------------------------------
     shapes = {}
-    for name, batch in (("mint", 64), ("freeze_5", 32), ("transfer_3x5", 32), ("transfer_5x5", 16), ("transfer_2x2_batch_1024", 1024)):
+    for name, batch in (("mint", 256), ("freeze_5", 128), ("transfer_3x5", 128), ("transfer_5x5", 64), ("transfer_2x2_batch_1024", 1024)):
         workload = "transfer_2x2" if name.endswith("1024") else name
         circ, circs, wires, pubs, bl = build_workload(workload, witnesses=2)
         srs = plonk.PlonkKzgSnark.universal_setup(ctx, circ.n + 2, TAU)

@@ -220,7 +220,13 @@ int capgpu_fr_rand_from_words(const uint64_t* words, size_t n_words, uint64_t* o
  * finalize_for_arithmetization); blinders: the 17 field elements the prover draws from its
  * RNG, in draw order (Montgomery, exactly the limbs `Fr::rand` returns);
  * ext_msg: `extra_transcript_init_msg` (may be NULL).  The Fiat-Shamir transcript
- * (jf-plonk SolidityTranscript, Keccak-256) is computed on the host inside the call. */
+ * (jf-plonk SolidityTranscript, Keccak-256) is computed on the host inside the call.
+ * COMPATIBILITY NOTE: the transcript conventions of the fused entry points (capgpu_prove*, the batch
+ * and queue calls) are this library's restatement of jf-plonk 0.1.2 @ bcd92b2c (vk field order,
+ * little-endian lengths, compressed G1, 48-byte challenge reduction); no upstream vector pins them
+ * yet (tests/test_replay.py does as soon as a reference-made CAPFIX01 fixture is present).  Until
+ * then only the round-level API below, driven by the caller's own `SolidityTranscript`, is
+ * upstream-compatible by construction. */
 int capgpu_prove(capgpu_ctx* ctx, const capgpu_pk* pk, const uint64_t* wires, const uint64_t* pub_inputs,
                  const uint64_t* blinders, const uint8_t* ext_msg, size_t ext_msg_len, capgpu_proof* out);
 
