@@ -587,11 +587,12 @@ struct MsmTuning {
   size_t strip_min;    // buckets per launch from which the single-lane strip form of its first stage is used
   uint32_t flat_smin;  // fewest entries per thread of the flat accumulation
   int window_min;      // smallest automatic window for n >= 2^12
+  size_t flat_min_entries;  // fewest sorted entries of a launch for the flat accumulation
 };
 
 static const MsmTuning& msm_tuning() {
   static MsmTuning t = [] {
-    MsmTuning x{0, 65536, 128, true, true, true, (size_t)1 << 17, 8, 15};  // measured: a 2^17-point MSM runs 7 % faster with 2 lanes per bucket than with 4
+    MsmTuning x{0, 65536, 128, true, true, true, (size_t)1 << 17, 8, 15, (size_t)1 << 16};  // measured: a 2^17-point MSM runs 7 % faster with 2 lanes per bucket than with 4
     if (const char* e = getenv("CAPGPU_RED_SEG")) x.red_seg = atoi(e);
     if (const char* e = getenv("CAPGPU_ACC_THREADS")) x.acc_threads = (size_t)atol(e);
     if (const char* e = getenv("CAPGPU_ACC_BLOCK")) x.acc_block = (unsigned)atoi(e);
@@ -601,6 +602,7 @@ static const MsmTuning& msm_tuning() {
     if (const char* e = getenv("CAPGPU_RED_STRIP_MIN")) x.strip_min = (size_t)atol(e);
     if (const char* e = getenv("CAPGPU_FLAT_SMIN")) x.flat_smin = (uint32_t)atoi(e);
     if (const char* e = getenv("CAPGPU_WINDOW_MIN")) x.window_min = atoi(e);
+    if (const char* e = getenv("CAPGPU_FLAT_MIN_ENTRIES")) x.flat_min_entries = (size_t)atol(e);
     return x;
   }();
   return t;
@@ -640,7 +642,7 @@ static void launch_accumulate(capgpu_ctx* ctx, const capgpu_srs* srs, size_t K, 
 }
 
 void msm_device(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const Fr* scalars, size_t n, size_t stride,
-                size_t batch, bool scalars_mont, G1Affine* out_dev, bool latency, size_t part, size_t parts) {
+                size_t batch, bool scalars_mont, G1Affine* out_dev, bool latency, size_t part, size_t parts, G1XYZZ* out_xyzz) {
   if (batch == 0) return;
   if (base_off + n > srs->n) throw CodeError{CAPGPU_ERR_SRS_TOO_SMALL};
   CAPGPU_REQUIRE(srs->device == ctx->device, "SRS lives on another device");
@@ -649,8 +651,10 @@ void msm_device(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const F
   const size_t K = srs->K / parts;
   const uint32_t lo = (uint32_t)(part * K);
   const int W = srs->W, c = srs->c;
+  CAPGPU_REQUIRE(!out_xyzz || (srs->K / parts >= 512 && msm_tuning().tree), "XYZZ slice results need at least 512 buckets per slice");
   if (n == 0) {
-    CAPGPU_CUDA(cudaMemsetAsync(out_dev, 0, batch * sizeof(G1Affine), ctx->stream));
+    if (out_xyzz) CAPGPU_CUDA(cudaMemsetAsync(out_xyzz, 0, batch * sizeof(G1XYZZ), ctx->stream));
+    else CAPGPU_CUDA(cudaMemsetAsync(out_dev, 0, batch * sizeof(G1Affine), ctx->stream));
     return;
   }
   ctx->msm_digits.reserve(2 * batch * W * n * sizeof(int32_t));
@@ -676,7 +680,7 @@ void msm_device(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const F
   // one-wave launches in the low-latency schedule: equal chunks of sorted entries per thread
   const size_t wave_threads = (size_t)ctx->sm_count * 4 * 128;
   const size_t ee = es / parts;  // expected entries of this bucket-range slice
-  const bool flat = latency && msm_tuning().flat && batch * K * lpb <= wave_threads && ee >= 4 * wave_threads;
+  const bool flat = latency && msm_tuning().flat && batch * K * lpb <= wave_threads && ee >= msm_tuning().flat_min_entries;
 
   {
   ProfScope prof_sort(ctx, PROF_MSM_SORT, (double)batch * W * n);
@@ -801,9 +805,9 @@ void msm_device(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const F
     {
       dim3 grid((unsigned)nplanes, (unsigned)batch);
       if (batch * nplanes <= (size_t)ctx->sm_count)
-        msm_red_planes<128><<<grid, 512, 0, ctx->stream>>>(sums, R, row0, nplanes, planes, ctx->msm_ticket.as<uint32_t>(), out_dev);
+        msm_red_planes<128><<<grid, 512, 0, ctx->stream>>>(sums, R, row0, nplanes, planes, ctx->msm_ticket.as<uint32_t>(), out_dev, out_xyzz);
       else
-        msm_red_planes<32><<<grid, 128, 0, ctx->stream>>>(sums, R, row0, nplanes, planes, ctx->msm_ticket.as<uint32_t>(), out_dev);
+        msm_red_planes<32><<<grid, 128, 0, ctx->stream>>>(sums, R, row0, nplanes, planes, ctx->msm_ticket.as<uint32_t>(), out_dev, out_xyzz);
       CAPGPU_LAUNCH_CHECK(ctx);
     }
     return;
@@ -1052,6 +1056,23 @@ extern "C" int capgpu_msm_g1_dev_part(capgpu_ctx* ctx, const capgpu_srs* srs, si
   if (!ctx || !srs || !d_out_xy || (!d_scalars && n)) return CAPGPU_ERR_ARG;
   return guarded(ctx, [&] {
     msm_device(ctx, srs, base_off, (const Fr*)d_scalars, n, n, 1, scalars_mont != 0, (G1Affine*)d_out_xy, true, part, parts);
+  });
+}
+
+extern "C" int capgpu_msm_g1_dev_part_xyzz(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const void* d_scalars, size_t n,
+                                           int scalars_mont, size_t part, size_t parts, void* d_out_xyzz) {
+  if (!ctx || !srs || !d_out_xyzz || (!d_scalars && n)) return CAPGPU_ERR_ARG;
+  return guarded(ctx, [&] {
+    msm_device(ctx, srs, base_off, (const Fr*)d_scalars, n, n, 1, scalars_mont != 0, nullptr, true, part, parts, (G1XYZZ*)d_out_xyzz);
+  });
+}
+
+extern "C" int capgpu_g1_sum_xyzz_dev(capgpu_ctx* ctx, const void* d_points_xyzz, size_t count, void* d_out_xy) {
+  if (!ctx || !d_out_xy || (!d_points_xyzz && count)) return CAPGPU_ERR_ARG;
+  return guarded(ctx, [&] {
+    CAPGPU_REQUIRE(count <= (1u << 16), "too many points");
+    g1_sum_xyzz_kernel<<<1, RED_THREADS, 0, ctx->stream>>>((const G1XYZZ*)d_points_xyzz, (uint32_t)count, (G1Affine*)d_out_xy);
+    CAPGPU_LAUNCH_CHECK(ctx);
   });
 }
 

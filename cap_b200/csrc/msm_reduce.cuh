@@ -224,12 +224,12 @@ __global__ void __launch_bounds__(128, 4) msm_red_sums_lane(const G1XYZZ* __rest
 }
 
 // Plane p (blockIdx.x) of vector b (blockIdx.y): Z_p, then 2^p * Z_p -> planes[b][p]; the last CTA of a vector
-// (ticket[b], self-resetting) folds the planes and writes the affine result.  QUADS lane quads per CTA: 128 for a
+// (ticket[b], self-resetting) folds the planes and writes the affine result (or, for out_xyzz, the XYZZ sum).  QUADS lane quads per CTA: 128 for a
 // lone MSM (shortest chain), 32 when many vectors share the launch (four CTAs per SM).
 template <int QUADS>
 __global__ void __launch_bounds__(4 * QUADS, (QUADS <= 32 ? 4 : 1)) msm_red_planes(const G1XYZZ* __restrict__ sums, size_t R, uint32_t row0,
                                                                                   int nplanes, G1XYZZ* planes, uint32_t* ticket,
-                                                                                  G1Affine* out) {
+                                                                                  G1Affine* out, G1XYZZ* out_xyzz) {
   __shared__ G1XYZZ T[QUADS];
   __shared__ uint32_t last_s;
   const uint32_t role = quad_role();
@@ -297,9 +297,37 @@ __global__ void __launch_bounds__(4 * QUADS, (QUADS <= 32 ? 4 : 1)) msm_red_plan
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    out[b] = xyzz_to_affine(T[0]);
+    if (out_xyzz) out_xyzz[b] = T[0];  // slice of a split MSM: the fold across GPUs converts once
+    else out[b] = xyzz_to_affine(T[0]);
     ticket[b] = 0;
   }
+}
+
+
+// Fold of the slice results of a split MSM (XYZZ, one per GPU, gathered over NVLink): quad tree + one inversion.
+__global__ void __launch_bounds__(RED_THREADS) g1_sum_xyzz_kernel(const G1XYZZ* __restrict__ pts, uint32_t count, G1Affine* out) {
+  __shared__ G1XYZZ T[RED_TILE];
+  const uint32_t role = quad_role();
+  const int g = threadIdx.x >> 2;
+  const int g0 = (threadIdx.x >> 5) * 8;
+  {
+    G1XYZZ x = (uint32_t)g < count ? pts[g] : G1XYZZ::inf();
+    st_xyzz_quad(&T[g], x, role);
+    __syncwarp();
+    for (uint32_t i = g + RED_TILE; __any_sync(0xffffffffu, i < count); i += RED_TILE) {
+      xyzz_add_quad_mem(&T[g], i < count ? pts + i : &g_xyzz_inf, &T[g], true, role);
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  for (int w = RED_TILE / 2; w >= 1; w >>= 1) {
+    if (g0 < w) {
+      const bool on = g < w;
+      xyzz_add_quad_mem(on ? &T[g] : &g_xyzz_inf, on ? &T[g + w] : &g_xyzz_inf, &T[g], on, role);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *out = xyzz_to_affine(T[0]);
 }
 
 }  // namespace capgpu

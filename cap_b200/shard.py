@@ -53,8 +53,8 @@ class SplitMsm:
     BUCKET RANGE (BASELINE north_star: "a single large MSM can be split ... with partial sums reduced
     over NVLink").  Every rank holds the whole commit key `srs` and the whole scalar vector; rank r
     sorts, accumulates and reduces only the buckets of slice r (capgpu_msm_g1_dev_part), so all three
-    phases shrink with the number of GPUs.  The 64-byte slice results are exchanged with one NCCL
-    all-gather and folded with EC additions (capgpu_g1_sum_dev).  Everything -- the MSM kernels, the
+    phases shrink with the number of GPUs.  The slice results (128-byte XYZZ sums) are exchanged with one NCCL
+    all-gather and folded with EC additions and ONE conversion to affine (capgpu_g1_sum_xyzz_dev).  Everything -- the MSM kernels, the
     all-gather and the fold -- is enqueued on the context's stream (it is made torch's current stream
     for the collective), with no host synchronisation in between; the caller synchronises once."""
 
@@ -67,8 +67,12 @@ class SplitMsm:
         self.parts = bucket_parts(self.world)
         self.stream = torch.cuda.ExternalStream(ctx.stream)
         dev = torch.device("cuda", ctx.device)
-        self.part = torch.zeros(8, dtype=torch.int64, device=dev)
-        self.gathered = torch.zeros((self.world, 8), dtype=torch.int64, device=dev)
+        # keys of >= 2^12 points have >= 2^14 buckets: slices then hand over their XYZZ sum (128 B) and only the
+        # fold converts to affine (one inversion on the critical path instead of two)
+        self.xyzz = srs.size >= (1 << 12) and self.world > 1
+        words = 16 if self.xyzz else 8
+        self.part = torch.zeros(words, dtype=torch.int64, device=dev)
+        self.gathered = torch.zeros((self.world, words), dtype=torch.int64, device=dev)
         self.out = torch.zeros(8, dtype=torch.int64, device=dev)
 
     def __call__(self, d_scalars, mont: bool = False):
@@ -80,14 +84,16 @@ class SplitMsm:
         from . import _lib
         lib, ctx = self.ctx.lib, self.ctx
         n = int(d_scalars.shape[0])
+        slice_fn = lib.capgpu_msm_g1_dev_part_xyzz if self.xyzz else lib.capgpu_msm_g1_dev_part
         if self.rank < self.parts:
-            _lib.check(lib.capgpu_msm_g1_dev_part(ctx.h, self.srs.h, 0, c_void_p(d_scalars.data_ptr()), n, int(mont), self.rank, self.parts,
-                                                  c_void_p(self.part.data_ptr())), ctx.h)
+            _lib.check(slice_fn(ctx.h, self.srs.h, 0, c_void_p(d_scalars.data_ptr()), n, int(mont), self.rank, self.parts,
+                                c_void_p(self.part.data_ptr())), ctx.h)
         if self.world == 1:
             return self.part
         with torch.cuda.stream(self.stream):
             if self.rank >= self.parts:
                 self.part.zero_()
             dist.all_gather_into_tensor(self.gathered, self.part)
-        _lib.check(lib.capgpu_g1_sum_dev(ctx.h, c_void_p(self.gathered.data_ptr()), self.world, c_void_p(self.out.data_ptr())), ctx.h)
+        fold = lib.capgpu_g1_sum_xyzz_dev if self.xyzz else lib.capgpu_g1_sum_dev
+        _lib.check(fold(ctx.h, c_void_p(self.gathered.data_ptr()), self.world, c_void_p(self.out.data_ptr())), ctx.h)
         return self.out

@@ -123,6 +123,13 @@ int capgpu_msm_g1_adhoc(capgpu_ctx* ctx, const uint64_t* points_xy, const uint64
  * fold a point-range-split MSM: each GPU runs capgpu_msm_g1_dev over its slice of the bases, the
  * 64-byte partial results are gathered over NVLink (NCCL all-gather) and added here. */
 int capgpu_g1_sum_dev(capgpu_ctx* ctx, const void* d_points_xy, size_t count, void* d_out_xy);
+/* Same split with the slice result left in extended Jacobian XYZZ form (X, Y, ZZ, ZZZ: 4 x 4 u64 Montgomery,
+ * x = X / ZZ, y = Y / ZZZ, ZZ = 0 for infinity) and its fold: the slices skip their own conversion to affine
+ * (one field inversion each) and the fold of the gathered 128-byte results converts once.  Needs at least
+ * 512 buckets per slice (windows of >= 10 + log2(parts) bits: every SRS of >= 2^12 points). */
+int capgpu_msm_g1_dev_part_xyzz(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const void* d_scalars, size_t n,
+                                int scalars_mont, size_t part, size_t parts, void* d_out_xyzz);
+int capgpu_g1_sum_xyzz_dev(capgpu_ctx* ctx, const void* d_points_xyzz, size_t count, void* d_out_xy);
 
 /* ---- radix-2 NTT over Fr -----------------------------------------------------------------
  * Replaces ark-poly 0.3.0 `Radix2EvaluationDomain::{fft, ifft, coset_fft, coset_ifft}`

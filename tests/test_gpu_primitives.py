@@ -218,6 +218,27 @@ def test_msm_at_bench_sizes(ctx, log_n):
     srs.close()
 
 
+@pytest.mark.parametrize("log_n,batch", [(14, 12), (15, 9)])
+def test_msm_large_batches_use_the_strip_reduction(ctx, log_n, batch):
+    """Batched launches with >= 2^17 buckets in flight take the single-lane strip / per-sum form of the bucket
+    reduction (msm_red_strips, msm_red_sums_lane, 32-quad plane CTAs): every vector of the batch against
+    p(tau) G, with an all-zero vector, a vector of ones and a single-entry vector among them."""
+    n = (1 << log_n) + 3
+    srs = device.Srs(ctx, tau_mont=field.fr_to_mont_array([TAU])[0], size=n)
+    g = np.random.default_rng(100 + log_n)
+    a = g.integers(0, 1 << 62, size=(batch, n, 4), dtype=np.uint64)
+    a[..., 3] &= (1 << 60) - 1
+    a[1] = 0
+    a[2] = 0
+    a[2, :, 0] = 1
+    a[3] = 0
+    a[3, n - 1] = a[0, n - 1]
+    res = field.g1_from_mont_array(srs.msm(a, mont=False))
+    for i in range(batch):
+        assert res[i] == omsm.kzg_commit_tau(field.fr_from_raw_array(a[i]), TAU), i
+    srs.close()
+
+
 def test_srs_upload_from_compressed_points(ctx):
     """ark-serialize compressed G1 (the on-disk form of the reference's SRS / key files,
     src/parameters.rs:557-592): decompression on the device reproduces the points, including
@@ -261,6 +282,17 @@ def test_msm_bucket_range_slices_sum_to_the_msm(ctx, log_n, parts):
         _lib.check(ctx.lib.capgpu_g1_sum_dev(ctx.h, c_void_p(outs.data_ptr()), parts, c_void_p(total.data_ptr())), ctx.h)
         ctx.sync()
         assert np.array_equal(total.cpu().numpy().view(np.uint64), want)
+        # the same slices left in XYZZ form (128 B each) and folded with one conversion to affine
+        xy = torch.zeros((parts, 16), dtype=torch.int64, device="cuda")
+        rcs = [ctx.lib.capgpu_msm_g1_dev_part_xyzz(ctx.h, srs.h, 0, c_void_p(d.data_ptr()), n, 0, p, parts, c_void_p(xy[p].data_ptr())) for p in range(parts)]
+        if log_n >= 12:
+            assert rcs == [0] * parts
+            total2 = torch.zeros(8, dtype=torch.int64, device="cuda")
+            _lib.check(ctx.lib.capgpu_g1_sum_xyzz_dev(ctx.h, c_void_p(xy.data_ptr()), parts, c_void_p(total2.data_ptr())), ctx.h)
+            ctx.sync()
+            assert np.array_equal(total2.cpu().numpy().view(np.uint64), want)
+        else:
+            assert rcs == [-2] * parts  # fewer than 512 buckets per slice: affine slices only
     assert ctx.lib.capgpu_msm_g1_dev_part(ctx.h, srs.h, 0, c_void_p(d.data_ptr()), n, 0, 3, 3, c_void_p(total.data_ptr())) == -2
     srs.close()
 
