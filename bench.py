@@ -62,6 +62,8 @@ def parse_args():
     ap.add_argument("--fixture", default=None, help="CAPFIX01 replay fixture (rust/parity-dump): prove ITS key / witness / RNG words instead of the "
                                                      "synthetic workload and compare the proof bytes with the recorded ones")
     ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE config 2-5 measurements (other note shapes, kernel sweeps, 1024-note batch)")
+    ap.add_argument("--csv", default=None, help="also write the per-note-shape results as a CSV in the column layout of the reference's benches "
+                    "(save_result_to_file_simple, /root/reference/src/bench_utils/mod.rs:236-253)")
     ap.add_argument("--no-extras", action="store_true", help="skip roofline / MSM-latency / cpu_baseline side measurements")
     return ap.parse_args()
 
@@ -303,9 +305,48 @@ def run_capgpu(args):
         line.update(side_measurements(args, torch, ctxs, pk, srs, circ, wires_dev, wires, pubs, bl, prove_one, world, prove_group0))
     if rank == 0:
         emit(json.dumps(line))
+        if args.csv:
+            write_reference_csv(args.csv, line, circ, args)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+# the reference's benches write /tmp/<note>_cap_benchmark.csv with these columns (src/bench_utils/mod.rs:236-253);
+# shapes: (transaction, inputs, outputs, tree height) of the CAP circuit whose domain size the synthetic shape copies
+# (src/utils/mod.rs:137-193)
+CSV_HEADERS = ["TRANSACTION", "N_THREADS", "FUNCTION", "N_INPUTS", "N_OUTPUTS", "TREE_HEIGHT", "DOMAIN_SIZE", "N_CONSTRAINTS", "UTILITY_RATIO(%)",
+               "TRANSFER_NOTE_SIZE (KB)", "PROVING_KEY_SIZE (KB)", "VERIFYING_KEY_SIZE (KB)", "TIME (ms)"]
+CSV_SHAPES = {"transfer_2x2": ("transfer_note", 2, 2, 26), "mint": ("mint_note", 1, 2, 26), "freeze_5": ("freeze_note", 5, 5, 26),
+              "transfer_3x5": ("transfer_note", 3, 5, 26), "transfer_5x5": ("transfer_note", 5, 5, 26)}
+
+
+def write_reference_csv(path, line, circ, args):
+    """One row per measured note shape, FUNCTION = "Gen" (proof generation), TIME = ms per proof at the measured
+    throughput of one GPU.  N_CONSTRAINTS / UTILITY_RATIO describe the synthetic circuit (all rows of the domain are
+    gates); the note size is the proof alone (13 compressed G1 + 10 Fr), the key sizes are the CanonicalSerialize sizes
+    of a key of this shape (18 polynomials of n coefficients + n + 3 compressed G1 + the verifying key)."""
+    import csv
+    rows = []
+    threads = line["config"].get("host_threads_per_gpu", args.ctxs)
+
+    def row(name, log_n, ms):
+        tx, nin, nout, depth = CSV_SHAPES[name]
+        n = 1 << log_n
+        pk_kb = (18 * (8 + 32 * n) + 8 + 32 * (n + 3) + 8 * 3 + 32 * (18 + 5) + 96 + 3 * 64) / 1024
+        vk_kb = (8 * 3 + 32 * (18 + 5) + 96 + 3 * 64) / 1024
+        return [tx, threads, "Gen", nin, nout, depth, n, n, "100.00", "%.3f" % ((13 * 32 + 10 * 32) / 1024), "%.1f" % pk_kb, "%.3f" % vk_kb,
+                "%.4f" % ms]
+
+    per_gpu = line["value"] / max(line["n_gpus"], 1)
+    rows.append(row(args.workload, circ.log_n, 1e3 / per_gpu))
+    for name, v in line.get("configs", {}).get("note_shapes", {}).items():
+        if name in CSV_SHAPES:
+            rows.append(row(name, int(v["domain"].split("^")[1]), v["ms_per_proof"]))
+    with open(path, "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerow(CSV_HEADERS)
+        w.writerows(rows)
 
 
 def split_msm_measurement(torch, dist, ctx, world):
