@@ -482,6 +482,16 @@ def side_measurements(args, torch, ctxs, pk, srs, circ, wires_dev, wires, pubs, 
                   "gbutterflies_per_s": 7 * (m / 2) * log_m / (ntt_ms * 1e-3) * 1e-9,
                   "frac_of_fmul_microbench": 7 * (m / 2) * log_m / (ntt_ms * 1e-3) * 1e-9 / calib["gfmul_per_s"]}
     del a, b
+    # the same transforms as the prover issues them: one launch pair for a whole lockstep group (7 x group polynomials)
+    gb = 7 * args.group
+    a = torch.randint(0, 1 << 60, (gb, m, 4), dtype=torch.int64, device="cuda", generator=g)
+    b = torch.empty_like(a)
+    grp_ms = time_on_stream(lambda: _lib.check(lib.capgpu_ntt_dev(ctx.h, c_void_p(a.data_ptr()), m, c_void_p(b.data_ptr()), log_m, gb, 0, 1), ctx.h), reps=5)
+    out["ntt"]["lockstep_group"] = {"size": f"{gb} x 2^{log_m} coset NTT (7 per proof x group of {args.group})", "ms": grp_ms, "ms_per_7": grp_ms / args.group,
+                                    "gbutterflies_per_s": gb * (m / 2) * log_m / (grp_ms * 1e-3) * 1e-9,
+                                    "frac_of_fmul_microbench": gb * (m / 2) * log_m / (grp_ms * 1e-3) * 1e-9 / calib["gfmul_per_s"],
+                                    "note": "ncu (profiles/r2_ncu_ntt_group8_raw.csv): sm__pipe_fmaheavy_cycles_active 90 % / 88 % of elapsed in the two passes"}
+    del a, b
     n17 = 1 << 17
     srs17 = device.Srs(ctx, tau_mont=field.fr_to_mont_array([TAU % field.R])[0], size=n17)
     sc = torch.randint(-(1 << 63), (1 << 63) - 1, (n17, 4), dtype=torch.int64, device="cuda", generator=g)

@@ -4,6 +4,7 @@
 // (X - z).  Each replaces a CPU loop of jf-plonk 0.1.2 `Prover` / jf-relation 0.1.2
 // `PlonkCircuit` behind /root/reference/src/proof/transfer.rs:181 (names cited per kernel).
 #include "poly.cuh"
+#include <stdlib.h>
 
 namespace capgpu {
 
@@ -170,7 +171,8 @@ __device__ __forceinline__ Fr pow5(const Fr& w) {
   return fp_mul(fp_sqr(w2), w);
 }
 
-__global__ void __launch_bounds__(128) quotient_kernel(const Fr* __restrict__ coset /*7 x m: w0..w4, pi, z*/, const Fr* __restrict__ sel /*13 x m*/,
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) quotient_kernel(const Fr* __restrict__ coset /*7 x m: w0..w4, pi, z*/, const Fr* __restrict__ sel /*13 x m*/,
                                                        const Fr* __restrict__ sig /*5 x m*/, const Fr* __restrict__ xs /*m*/,
                                                        const Fr* __restrict__ l1inv /*m*/, const Fr* __restrict__ zh_inv /*8*/, size_t m,
                                                        int G, const QuotArgs* __restrict__ argv, Fr* out) {
@@ -217,7 +219,13 @@ __global__ void __launch_bounds__(128) quotient_kernel(const Fr* __restrict__ co
 void quotient_evals(capgpu_ctx* ctx, const Fr* coset, const Fr* sel, const Fr* sig, const Fr* xs, const Fr* l1inv, const Fr* zh_inv,
                     size_t m, int G, const QuotArgs* args, Fr* out) {
   ProfScope prof(ctx, PROF_QUOTIENT, (double)m * G);
-  quotient_kernel<<<dim3(ceil_div(m, 128), G), 128, 0, ctx->stream>>>(coset, sel, sig, xs, l1inv, zh_inv, m, G, args, out);
+  // resident CTAs per SM (register cap): 2 = 176 registers (ncu: 2 warps per scheduler, multiplier busy 65 %; 507 proofs/s), 3 / 4 (525 / 530 proofs/s) trade
+  // a few spills for occupancy; CAPGPU_QUOT_MINB selects for A/B runs
+  static const int minb = [] { const char* e = getenv("CAPGPU_QUOT_MINB"); int v = e ? atoi(e) : 4; return v < 2 ? 2 : (v > 4 ? 4 : v); }();
+  const dim3 grid(ceil_div(m, 128), G);
+  if (minb == 2) quotient_kernel<2><<<grid, 128, 0, ctx->stream>>>(coset, sel, sig, xs, l1inv, zh_inv, m, G, args, out);
+  else if (minb == 3) quotient_kernel<3><<<grid, 128, 0, ctx->stream>>>(coset, sel, sig, xs, l1inv, zh_inv, m, G, args, out);
+  else quotient_kernel<4><<<grid, 128, 0, ctx->stream>>>(coset, sel, sig, xs, l1inv, zh_inv, m, G, args, out);
   CAPGPU_LAUNCH_CHECK(ctx);
 }
 
