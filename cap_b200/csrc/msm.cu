@@ -638,7 +638,10 @@ static void launch_accumulate2(capgpu_ctx* ctx, const capgpu_srs* srs, size_t K,
 template <int LPB>
 static void launch_accumulate(capgpu_ctx* ctx, const capgpu_srs* srs, size_t K, const uint32_t* entries, const uint32_t* offsets,
                               const uint32_t* order, G1XYZZ* buckets, size_t entries_stride, size_t batch, uint32_t heavy_thr) {
-  launch_accumulate2<LPB, 4>(ctx, srs, K, entries, offsets, order, buckets, entries_stride, batch, heavy_thr);
+  // resident CTAs per SM (register cap) of the one-lane-per-bucket kernel: CAPGPU_ACC_MINB = 4 (108 registers) | 5 (102)
+  static const int minb = [] { const char* e = getenv("CAPGPU_ACC_MINB"); return e ? atoi(e) : 5; }();  // measured: 0.986 -> 0.976 ms per proof
+  if (LPB == 1 && minb == 5) launch_accumulate2<LPB, 5>(ctx, srs, K, entries, offsets, order, buckets, entries_stride, batch, heavy_thr);
+  else launch_accumulate2<LPB, 4>(ctx, srs, K, entries, offsets, order, buckets, entries_stride, batch, heavy_thr);
 }
 
 void msm_device(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const Fr* scalars, size_t n, size_t stride,
