@@ -23,6 +23,7 @@ EXPORTS = [
     "capgpu_ctx_set_group", "capgpu_pk_info", "capgpu_prove_batch_dev", "capgpu_queue_create", "capgpu_queue_destroy", "capgpu_submit", "capgpu_poll", "capgpu_wait", "capgpu_queue_stats",
     "capgpu_sha256", "capgpu_srs_load_serialized", "capgpu_pk_load_serialized", "capgpu_proof_serialize", "capgpu_fr_rand_from_words", "capgpu_msm_g1_dev_part",
     "capgpu_curve_msm_g1", "capgpu_curve_fq_op", "capgpu_msm_g1_dev_part_xyzz", "capgpu_g1_sum_xyzz_dev",
+    "capgpu_msm_g1_dev_part_peer", "capgpu_g1_sum_xyzz_wait_dev",
 ]
 
 
@@ -81,6 +82,8 @@ def load() -> ctypes.CDLL:
         "capgpu_g1_sum_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
         "capgpu_msm_g1_dev_part_xyzz": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_int, c_size_t, c_size_t, c_void_p]),
         "capgpu_g1_sum_xyzz_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+        "capgpu_msm_g1_dev_part_peer": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_int, c_size_t, c_size_t, c_void_p, c_void_p, c_size_t, c_uint]),
+        "capgpu_g1_sum_xyzz_wait_dev": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_size_t, c_uint, c_void_p]),
         "capgpu_srs_destroy": (None, [c_void_p]),
         "capgpu_srs_size": (c_size_t, [c_void_p]),
         "capgpu_msm_g1": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, c_int, c_void_p]),

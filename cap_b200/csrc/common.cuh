@@ -168,6 +168,7 @@ const Fr* domain_omega_powers(capgpu_ctx* ctx, unsigned log_n);  // omega^j, j <
 capgpu_srs* srs_lagrange(capgpu_ctx* ctx, const capgpu_srs* srs, unsigned log_n, const Fr* omega_pows, const Fr& n_inv);
 void msm_device(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const Fr* scalars, size_t n, size_t stride,
                 size_t batch, bool scalars_mont, G1Affine* out_dev, bool latency = false, size_t part = 0, size_t parts = 1,
-                G1XYZZ* out_xyzz = nullptr);  // out_xyzz: write the XYZZ sums instead of affine points (slices of a split MSM)
+                G1XYZZ* out_xyzz = nullptr,          // write the XYZZ sums instead of affine points (slices of a split MSM)
+                const struct PeerOut* peer = nullptr);  // ... or deliver the sum into peer-mapped memory (msm_reduce.cuh)
 
 }  // namespace capgpu

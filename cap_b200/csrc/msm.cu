@@ -645,8 +645,12 @@ static void launch_accumulate(capgpu_ctx* ctx, const capgpu_srs* srs, size_t K, 
 }
 
 void msm_device(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const Fr* scalars, size_t n, size_t stride,
-                size_t batch, bool scalars_mont, G1Affine* out_dev, bool latency, size_t part, size_t parts, G1XYZZ* out_xyzz) {
+                size_t batch, bool scalars_mont, G1Affine* out_dev, bool latency, size_t part, size_t parts, G1XYZZ* out_xyzz,
+                const PeerOut* peer) {
   if (batch == 0) return;
+  PeerOut po;
+  po.n = 0;
+  if (peer) po = *peer;
   if (base_off + n > srs->n) throw CodeError{CAPGPU_ERR_SRS_TOO_SMALL};
   CAPGPU_REQUIRE(srs->device == ctx->device, "SRS lives on another device");
   CAPGPU_REQUIRE(parts >= 1 && part < parts && srs->K % parts == 0, "bucket-range split must divide the bucket count");
@@ -654,7 +658,8 @@ void msm_device(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const F
   const size_t K = srs->K / parts;
   const uint32_t lo = (uint32_t)(part * K);
   const int W = srs->W, c = srs->c;
-  CAPGPU_REQUIRE(!out_xyzz || (srs->K / parts >= 512 && msm_tuning().tree), "XYZZ slice results need at least 512 buckets per slice");
+  CAPGPU_REQUIRE(!(out_xyzz || po.n) || (srs->K / parts >= 512 && msm_tuning().tree), "XYZZ slice results need at least 512 buckets per slice");
+  CAPGPU_REQUIRE(po.n == 0 || (batch == 1 && n > 0), "peer delivery is for one non-empty scalar vector");
   if (n == 0) {
     if (out_xyzz) CAPGPU_CUDA(cudaMemsetAsync(out_xyzz, 0, batch * sizeof(G1XYZZ), ctx->stream));
     else CAPGPU_CUDA(cudaMemsetAsync(out_dev, 0, batch * sizeof(G1Affine), ctx->stream));
@@ -808,9 +813,9 @@ void msm_device(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const F
     {
       dim3 grid((unsigned)nplanes, (unsigned)batch);
       if (batch * nplanes <= (size_t)ctx->sm_count)
-        msm_red_planes<128><<<grid, 512, 0, ctx->stream>>>(sums, R, row0, nplanes, planes, ctx->msm_ticket.as<uint32_t>(), out_dev, out_xyzz);
+        msm_red_planes<128><<<grid, 512, 0, ctx->stream>>>(sums, R, row0, nplanes, planes, ctx->msm_ticket.as<uint32_t>(), out_dev, out_xyzz, po);
       else
-        msm_red_planes<32><<<grid, 128, 0, ctx->stream>>>(sums, R, row0, nplanes, planes, ctx->msm_ticket.as<uint32_t>(), out_dev, out_xyzz);
+        msm_red_planes<32><<<grid, 128, 0, ctx->stream>>>(sums, R, row0, nplanes, planes, ctx->msm_ticket.as<uint32_t>(), out_dev, out_xyzz, po);
       CAPGPU_LAUNCH_CHECK(ctx);
     }
     return;
@@ -1074,7 +1079,34 @@ extern "C" int capgpu_g1_sum_xyzz_dev(capgpu_ctx* ctx, const void* d_points_xyzz
   if (!ctx || !d_out_xy || (!d_points_xyzz && count)) return CAPGPU_ERR_ARG;
   return guarded(ctx, [&] {
     CAPGPU_REQUIRE(count <= (1u << 16), "too many points");
-    g1_sum_xyzz_kernel<<<1, RED_THREADS, 0, ctx->stream>>>((const G1XYZZ*)d_points_xyzz, (uint32_t)count, (G1Affine*)d_out_xy);
+    g1_sum_xyzz_kernel<<<1, RED_THREADS, 0, ctx->stream>>>((const G1XYZZ*)d_points_xyzz, (uint32_t)count, (G1Affine*)d_out_xy, nullptr, 0, 0);
+    CAPGPU_LAUNCH_CHECK(ctx);
+  });
+}
+
+extern "C" int capgpu_msm_g1_dev_part_peer(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const void* d_scalars, size_t n,
+                                           int scalars_mont, size_t part, size_t parts, void* const* peer_slots, void* const* peer_flags,
+                                           size_t n_peers, uint32_t epoch) {
+  if (!ctx || !srs || !d_scalars || !n || !peer_slots || !peer_flags || n_peers == 0 || n_peers > (size_t)MAX_PEERS) return CAPGPU_ERR_ARG;
+  return guarded(ctx, [&] {
+    PeerOut po;
+    po.n = (int)n_peers;
+    po.epoch = epoch;
+    for (size_t i = 0; i < n_peers; i++) {
+      CAPGPU_REQUIRE(peer_slots[i] && peer_flags[i], "null peer pointer");
+      po.slot[i] = (G1XYZZ*)peer_slots[i];
+      po.flag[i] = (uint32_t*)peer_flags[i];
+    }
+    msm_device(ctx, srs, base_off, (const Fr*)d_scalars, n, n, 1, scalars_mont != 0, nullptr, true, part, parts, nullptr, &po);
+  });
+}
+
+extern "C" int capgpu_g1_sum_xyzz_wait_dev(capgpu_ctx* ctx, const void* d_points_xyzz, const void* d_flags, size_t flag_stride_bytes,
+                                           size_t count, uint32_t epoch, void* d_out_xy) {
+  if (!ctx || !d_out_xy || !d_points_xyzz || !d_flags || count == 0 || count > (size_t)MAX_PEERS || flag_stride_bytes % 4) return CAPGPU_ERR_ARG;
+  return guarded(ctx, [&] {
+    g1_sum_xyzz_kernel<<<1, RED_THREADS, 0, ctx->stream>>>((const G1XYZZ*)d_points_xyzz, (uint32_t)count, (G1Affine*)d_out_xy,
+                                                            (const uint32_t*)d_flags, (uint32_t)(flag_stride_bytes / 4), epoch);
     CAPGPU_LAUNCH_CHECK(ctx);
   });
 }

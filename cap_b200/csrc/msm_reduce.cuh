@@ -41,6 +41,17 @@ struct FlatParts {
   size_t nthreads;
 };
 
+// Destinations of a split-MSM slice result in the peer-mapped memory of every GPU of the group (NVLink / NVSwitch):
+// the last reduction kernel stores its 128-byte XYZZ sum straight into slot[i] of peer i and then releases flag[i]
+// (system scope) - the exchange is fused into the kernel that produces the data, no collective launch follows.
+constexpr int MAX_PEERS = 16;
+struct PeerOut {
+  G1XYZZ* slot[MAX_PEERS];
+  uint32_t* flag[MAX_PEERS];
+  int n;
+  uint32_t epoch;
+};
+
 __device__ G1XYZZ g_xyzz_inf;  // zero-initialised: the point at infinity, operand of idle quads
 
 __device__ __forceinline__ G1XYZZ ldcg_xyzz(const G1XYZZ* p) {
@@ -229,7 +240,7 @@ __global__ void __launch_bounds__(128, 4) msm_red_sums_lane(const G1XYZZ* __rest
 template <int QUADS>
 __global__ void __launch_bounds__(4 * QUADS, (QUADS <= 32 ? 4 : 1)) msm_red_planes(const G1XYZZ* __restrict__ sums, size_t R, uint32_t row0,
                                                                                   int nplanes, G1XYZZ* planes, uint32_t* ticket,
-                                                                                  G1Affine* out, G1XYZZ* out_xyzz) {
+                                                                                  G1Affine* out, G1XYZZ* out_xyzz, PeerOut peer) {
   __shared__ G1XYZZ T[QUADS];
   __shared__ uint32_t last_s;
   const uint32_t role = quad_role();
@@ -297,21 +308,46 @@ __global__ void __launch_bounds__(4 * QUADS, (QUADS <= 32 ? 4 : 1)) msm_red_plan
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    if (out_xyzz) out_xyzz[b] = T[0];  // slice of a split MSM: the fold across GPUs converts once
-    else out[b] = xyzz_to_affine(T[0]);
+    if (peer.n > 0) {
+      // slice of a split MSM, exchange fused in: peer-mapped stores of the sum, then the flags (release, system scope)
+      const G1XYZZ v = T[0];
+      for (int i = 0; i < peer.n; i++) *peer.slot[i] = v;
+      __threadfence_system();
+      for (int i = 0; i < peer.n; i++) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(peer.flag[i]), "r"(peer.epoch) : "memory");
+    } else if (out_xyzz) {
+      out_xyzz[b] = T[0];  // slice of a split MSM: the fold across GPUs converts once
+    } else {
+      out[b] = xyzz_to_affine(T[0]);
+    }
     ticket[b] = 0;
   }
 }
 
 
 // Fold of the slice results of a split MSM (XYZZ, one per GPU, gathered over NVLink): quad tree + one inversion.
-__global__ void __launch_bounds__(RED_THREADS) g1_sum_xyzz_kernel(const G1XYZZ* __restrict__ pts, uint32_t count, G1Affine* out) {
+// flags != nullptr: first wait until every peer has delivered its slice for this epoch (acquire loads, system scope;
+// gives up after ~2 s so that a missing peer shows up as a wrong result, not as a hung GPU), then read the slots
+// around L1 (they were written by other GPUs).
+__global__ void __launch_bounds__(RED_THREADS) g1_sum_xyzz_kernel(const G1XYZZ* pts, uint32_t count, G1Affine* out, const uint32_t* flags,
+                                                                  uint32_t flag_stride, uint32_t epoch) {
   __shared__ G1XYZZ T[RED_TILE];
   const uint32_t role = quad_role();
   const int g = threadIdx.x >> 2;
   const int g0 = (threadIdx.x >> 5) * 8;
+  if (flags) {
+    if (threadIdx.x < count) {
+      const uint32_t* f = flags + (size_t)threadIdx.x * flag_stride;
+      const long long t0 = clock64();
+      uint32_t v;
+      do {
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+      } while (v != epoch && clock64() - t0 < 4000000000LL);
+    }
+    __syncthreads();
+    __threadfence_system();
+  }
   {
-    G1XYZZ x = (uint32_t)g < count ? pts[g] : G1XYZZ::inf();
+    G1XYZZ x = (uint32_t)g < count ? ldcg_xyzz(pts + g) : G1XYZZ::inf();
     st_xyzz_quad(&T[g], x, role);
     __syncwarp();
     for (uint32_t i = g + RED_TILE; __any_sync(0xffffffffu, i < count); i += RED_TILE) {

@@ -58,7 +58,10 @@ class SplitMsm:
     all-gather and the fold -- is enqueued on the context's stream (it is made torch's current stream
     for the collective), with no host synchronisation in between; the caller synchronises once."""
 
-    def __init__(self, ctx, srs):
+    def __init__(self, ctx, srs, exchange: str = "auto"):
+        """exchange: "peer" = slice results stored straight into every GPU's symmetric-memory buffer by the last
+        reduction kernel, flags released with system scope, the fold waits on the flags (no collective call);
+        "nccl" = one all-gather on the context stream; "auto" = peer when symmetric memory can be set up."""
         import torch
         import torch.distributed as dist
         self.ctx, self.srs = ctx, srs
@@ -74,16 +77,54 @@ class SplitMsm:
         self.part = torch.zeros(words, dtype=torch.int64, device=dev)
         self.gathered = torch.zeros((self.world, words), dtype=torch.int64, device=dev)
         self.out = torch.zeros(8, dtype=torch.int64, device=dev)
+        self.peer = None
+        self.epoch = 0
+        if self.xyzz and exchange in ("auto", "peer") and self.parts == self.world and self.world <= 16:
+            try:
+                self._setup_peer(torch, dist, dev)
+            except Exception:  # symmetric memory unavailable on this box: the collective path stays
+                if exchange == "peer":
+                    raise
+                self.peer = None
+
+    def _setup_peer(self, torch, dist, dev):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm_mem
+        # two alternating buffers of [parts slots of 16 x int64 | parts flags at 8-byte stride]
+        self.slot_words = 16 * self.parts
+        self.buf_words = self.slot_words + 16 * ((self.parts + 15) // 16)  # flags padded: every half stays 128-byte aligned
+        buf = symm_mem.empty(2 * self.buf_words, dtype=torch.int64, device=dev)
+        buf.zero_()
+        hdl = symm_mem.rendezvous(buf, dist.group.WORLD)
+        torch.cuda.synchronize()
+        dist.barrier()
+        ptrs = [int(p) for p in hdl.buffer_ptrs]
+        self.peer = {"buf": buf, "hdl": hdl, "ptrs": ptrs}
+        self.peer_args = []
+        for half in range(2):
+            base = half * self.buf_words * 8
+            slots = (ctypes.c_void_p * self.world)(*[p + base + self.rank * 128 for p in ptrs])
+            flags = (ctypes.c_void_p * self.world)(*[p + base + self.slot_words * 8 + self.rank * 8 for p in ptrs])
+            self.peer_args.append((slots, flags, buf.data_ptr() + base, buf.data_ptr() + base + self.slot_words * 8))
 
     def __call__(self, d_scalars, mont: bool = False):
         """d_scalars: CUDA int64 tensor (n, 4) on the context's GPU, identical on every rank.  Returns
-        a CUDA int64 tensor (8,) = x || y of the result (valid after ctx.sync())."""
+        a CUDA int64 tensor (8,) = x || y of the result (valid after ctx.sync()).  With the peer exchange the
+        ranks must not run more than one call ahead of each other (two alternating buffers)."""
         import torch
         import torch.distributed as dist
         from ctypes import c_void_p
         from . import _lib
         lib, ctx = self.ctx.lib, self.ctx
         n = int(d_scalars.shape[0])
+        if self.peer is not None:
+            self.epoch += 1
+            slots, flags, my_slots, my_flags = self.peer_args[self.epoch & 1]
+            _lib.check(lib.capgpu_msm_g1_dev_part_peer(ctx.h, self.srs.h, 0, c_void_p(d_scalars.data_ptr()), n, int(mont), self.rank, self.parts,
+                                                       slots, flags, self.world, self.epoch), ctx.h)
+            _lib.check(lib.capgpu_g1_sum_xyzz_wait_dev(ctx.h, c_void_p(my_slots), c_void_p(my_flags), 8, self.world, self.epoch,
+                                                       c_void_p(self.out.data_ptr())), ctx.h)
+            return self.out
         slice_fn = lib.capgpu_msm_g1_dev_part_xyzz if self.xyzz else lib.capgpu_msm_g1_dev_part
         if self.rank < self.parts:
             _lib.check(slice_fn(ctx.h, self.srs.h, 0, c_void_p(d_scalars.data_ptr()), n, int(mont), self.rank, self.parts,

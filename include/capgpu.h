@@ -130,6 +130,21 @@ int capgpu_g1_sum_dev(capgpu_ctx* ctx, const void* d_points_xy, size_t count, vo
 int capgpu_msm_g1_dev_part_xyzz(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const void* d_scalars, size_t n,
                                 int scalars_mont, size_t part, size_t parts, void* d_out_xyzz);
 int capgpu_g1_sum_xyzz_dev(capgpu_ctx* ctx, const void* d_points_xyzz, size_t count, void* d_out_xy);
+/* The same split with the exchange FUSED into the kernels, over peer-mapped memory (NVLink / NVSwitch), no
+ * collective call on the data path.  Every GPU owns a buffer of `parts` 128-byte slots and `parts` 32-bit flags that
+ * its peers can address (CUDA peer access / IPC / symmetric memory; the host side obtains the pointers, e.g. from
+ * torch.distributed._symmetric_memory).  capgpu_msm_g1_dev_part_peer computes slice `part` and its last kernel stores
+ * the XYZZ sum into peer_slots[i] (slot `part` of GPU i, i < n_peers <= 16; the GPU's own buffer included) and then
+ * releases peer_flags[i] = epoch with system scope.  capgpu_g1_sum_xyzz_wait_dev (on each GPU that wants the result)
+ * waits until all `count` flags of ITS buffer hold `epoch` (acquire, system scope; it gives up after about two
+ * seconds, leaving a wrong result rather than a hung GPU), then folds the slots and converts to affine once.
+ * Use a fresh epoch per MSM and alternate between two buffers, or synchronise the GPUs between MSMs: a peer that
+ * runs ahead would overwrite slots still being folded. */
+int capgpu_msm_g1_dev_part_peer(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const void* d_scalars, size_t n,
+                                int scalars_mont, size_t part, size_t parts, void* const* peer_slots, void* const* peer_flags,
+                                size_t n_peers, uint32_t epoch);
+int capgpu_g1_sum_xyzz_wait_dev(capgpu_ctx* ctx, const void* d_points_xyzz, const void* d_flags, size_t flag_stride_bytes,
+                                size_t count, uint32_t epoch, void* d_out_xy);
 
 /* ---- radix-2 NTT over Fr -----------------------------------------------------------------
  * Replaces ark-poly 0.3.0 `Radix2EvaluationDomain::{fft, ifft, coset_fft, coset_ifft}`

@@ -95,6 +95,8 @@ extern "C" {
     pub fn capgpu_calibrate(ctx: *mut capgpu_ctx, gimad_per_s: *mut f64, gimad_wide_per_s: *mut f64, gfmul_per_s: *mut f64) -> c_int;
     pub fn capgpu_msm_g1_dev_part_xyzz(ctx: *mut capgpu_ctx, srs: *const capgpu_srs, base_off: usize, d_scalars: *const c_void, n: usize, scalars_mont: c_int, part: usize, parts: usize, d_out_xyzz: *mut c_void) -> c_int;
     pub fn capgpu_g1_sum_xyzz_dev(ctx: *mut capgpu_ctx, d_points_xyzz: *const c_void, count: usize, d_out_xy: *mut c_void) -> c_int;
+    pub fn capgpu_msm_g1_dev_part_peer(ctx: *mut capgpu_ctx, srs: *const capgpu_srs, base_off: usize, d_scalars: *const c_void, n: usize, scalars_mont: c_int, part: usize, parts: usize, peer_slots: *const *mut c_void, peer_flags: *const *mut c_void, n_peers: usize, epoch: u32) -> c_int;
+    pub fn capgpu_g1_sum_xyzz_wait_dev(ctx: *mut capgpu_ctx, d_points_xyzz: *const c_void, d_flags: *const c_void, flag_stride_bytes: usize, count: usize, epoch: u32, d_out_xy: *mut c_void) -> c_int;
     // BLS12-381 (curve = 1) / BLS12-377 (curve = 2) G1 over 12-limb base fields (src/config.rs:86-114)
     pub fn capgpu_curve_msm_g1(ctx: *mut capgpu_ctx, curve: c_int, points_xy: *const u64, scalars: *const u64, n: usize, out_xy: *mut u64) -> c_int;
     pub fn capgpu_curve_fq_op(ctx: *mut capgpu_ctx, curve: c_int, op: c_int, a: *const u64, b: *const u64, out: *mut u64, count: usize) -> c_int;

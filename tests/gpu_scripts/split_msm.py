@@ -34,12 +34,16 @@ srs = device.Srs(ctx, tau_mont=field.fr_to_mont_array([TAU])[0], size=N)  # the 
 sc = np.random.default_rng(5).integers(0, 1 << 62, size=(N, 4), dtype=np.uint64)
 sc[:, 3] &= (1 << 60) - 1
 d_all = torch.from_numpy(sc.view(np.int64)).cuda()
-split = shard.SplitMsm(ctx, srs)
+split = shard.SplitMsm(ctx, srs)                        # peer-memory exchange when symmetric memory is available
+split_nccl = shard.SplitMsm(ctx, srs, exchange="nccl")  # one NCCL all-gather on the context stream
 
-res = split(d_all)
-ctx.sync()
-got = field.g1_from_mont_array(res.cpu().numpy().view(np.uint64))[0]
-ok = got == omsm.kzg_commit_tau(field.fr_from_raw_array(sc), TAU)
+want = omsm.kzg_commit_tau(field.fr_from_raw_array(sc), TAU)
+ok = True
+for s_ in (split, split_nccl, split):
+    res = s_(d_all)
+    ctx.sync()
+    dist.barrier()
+    ok = ok and field.g1_from_mont_array(res.cpu().numpy().view(np.uint64))[0] == want
 oks = [None] * world
 dist.all_gather_object(oks, bool(ok))
 
@@ -63,11 +67,13 @@ def timed(fn, reps):
 
 
 split_ms = timed(lambda: split(d_all), args.reps)
+nccl_ms = timed(lambda: split_nccl(d_all), args.reps)
 out1 = torch.zeros(8, dtype=torch.int64, device="cuda")
 single_ms = timed(lambda: _lib.check(ctx.lib.capgpu_msm_g1_dev(ctx.h, srs.h, 0, c_void_p(d_all.data_ptr()), N, 1, 0, c_void_p(out1.data_ptr())), ctx.h),
                   args.reps)
 if rank == 0:
-    line = {"n_gpus": world, "points": N, "split": "bucket range", "bucket_parts": split.parts, "split_msm_ms": split_ms,
+    line = {"n_gpus": world, "points": N, "split": "bucket range", "bucket_parts": split.parts, "exchange": "peer memory (symmetric memory, stores + flags fused into the kernels)" if split.peer is not None else "nccl all-gather",
+            "split_msm_ms": split_ms, "split_msm_ms_nccl_all_gather": nccl_ms,
             "single_gpu_msm_ms": single_ms, "speedup": single_ms / split_ms, "correct": all(oks)}
     print(json.dumps(line), flush=True)
     os.makedirs("gpurun_out", exist_ok=True)
