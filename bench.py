@@ -350,9 +350,10 @@ def write_reference_csv(path, line, circ, args):
 
 
 def split_msm_measurement(torch, dist, ctx, world):
-    """ONE 2^17-point MSM split by bucket range over the ranks (cap_b200.shard.SplitMsm: slice kernels,
-    NCCL all-gather of the 64-byte slice results over NVLink and the EC fold, all on the context
-    stream), beside the same MSM on one GPU.  CUDA events, max over ranks, median of 10."""
+    """ONE 2^17-point MSM split by bucket range over the ranks (cap_b200.shard.SplitMsm: slice kernels whose last
+    launch delivers the 128-byte XYZZ sums into peer-mapped memory of every GPU, or one NCCL all-gather where symmetric
+    memory is unavailable, then the EC fold, all on the context stream), beside the same MSM on one GPU.  CUDA events,
+    max over ranks, median of 10."""
     from ctypes import c_void_p
     from cap_b200 import _lib, device, field, shard
     n17 = 1 << 17
@@ -387,7 +388,9 @@ def split_msm_measurement(torch, dist, ctx, world):
     split_ms = timed(lambda: split(sc))
     single_ms = timed(lambda: _lib.check(ctx.lib.capgpu_msm_g1_dev(ctx.h, srs17.h, 0, c_void_p(sc.data_ptr()), n17, 1, 0, c_void_p(out1.data_ptr())), ctx.h))
     srs17.close()
-    return {"points": n17, "n_gpus": world, "split": "bucket range, slice results all-gathered over NCCL/NVLink on the context stream",
+    how = ("slice results stored into every GPU's symmetric-memory buffer by the last reduction kernel (peer-mapped stores + release flags over NVLink), "
+           "fold waits on the flags: no collective call") if split.peer is not None else "slice results all-gathered over NCCL/NVLink on the context stream"
+    return {"points": n17, "n_gpus": world, "split": "bucket range; " + how,
             "ms": split_ms, "single_gpu_ms": single_ms, "speedup": single_ms / split_ms, "equals_single_gpu_result": same}
 
 
