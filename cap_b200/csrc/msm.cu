@@ -802,7 +802,7 @@ void msm_device(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const F
       CAPGPU_LAUNCH_CHECK(ctx);
     }
     if (strips) {
-      dim3 grid(ceil_div(NS, 128), (unsigned)batch);
+      dim3 grid(ceil_div(4 * NS, 128), (unsigned)batch);
       msm_red_sums_lane<<<grid, 128, 0, ctx->stream>>>(rowpart, colpart, R, ncb, (int)nrb, sums);
       CAPGPU_LAUNCH_CHECK(ctx);
     } else {
