@@ -52,7 +52,7 @@ struct PeerOut {
   uint32_t epoch;
 };
 
-__device__ G1XYZZ g_xyzz_inf;  // zero-initialised: the point at infinity, operand of idle quads
+static __device__ G1XYZZ g_xyzz_inf;  // zero-initialised: the point at infinity, operand of idle quads
 
 __device__ __forceinline__ G1XYZZ ldcg_xyzz(const G1XYZZ* p) {
   G1XYZZ r;

@@ -11,5 +11,5 @@ ncu --metrics gpu__time_duration.sum --clock-control none -s $SKIP -c 200 --csv 
 ncu --set full --clock-control none -k regex:"quotient_kernel" -c 2 -o gpurun_out/r2_ncu_quot python tests/gpu_scripts/prof_group.py 8 1 > /dev/null 2>&1
 ncu -i gpurun_out/r2_ncu_quot.ncu-rep --page raw --csv > gpurun_out/r2_ncu_quotient_group8_raw.csv 2>/dev/null
 rm -f gpurun_out/r2_ncu_quot.ncu-rep
-ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_launches_msm_lone.csv python tests/gpu_scripts/r2b_msm.py 17:1 12:1 > /dev/null 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/r2_launches_msm_lone.csv python tests/gpu_scripts/msm_latency.py 17:1 12:1 > /dev/null 2>&1
 ls -la gpurun_out | tail -6
