@@ -564,7 +564,12 @@ def other_configs(args, torch, ctxs, calib, imad_peak):
         dev = [torch.from_numpy(w.view(np.int64)).cuda() for w in wires]
         ptrs = [dev[i % 2].data_ptr() for i in range(batch)]
         pp, bb, mm = [pubs[i % 2] for i in range(batch)], [bl[i % 2] for i in range(batch)], [b"cfg"] * batch
-        plonk.prove_batch_raw(ctxs, pk, ptrs, pp, bb, mm, on_device=True)  # warm-up: workspaces, tables
+        # warm-up: tables, and the group workspace of EVERY context (groups are dealt dynamically, so one batch call may
+        # leave a context without work and its multi-GB workspace would then be allocated inside the timed steps)
+        gw = min(args.group, batch)
+        for c in ctxs:
+            plonk.prove_batch_raw([c], pk, ptrs[:gw], pp[:gw], bb[:gw], mm[:gw], on_device=True)
+        plonk.prove_batch_raw(ctxs, pk, ptrs, pp, bb, mm, on_device=True)
         torch.cuda.synchronize()
         steps = 1 if batch >= 1024 else 3
         t0 = time.perf_counter()
