@@ -367,6 +367,11 @@ __global__ void __launch_bounds__(128, 4) msm_accumulate_flat(const G1Affine* __
   bool skip = bend - bs >= heavy_thr;  // heavy buckets are summed by msm_accumulate_heavy
   G1XYZZ acc = G1XYZZ::inf();
   G1XYZZ* bk = buckets + bi * K;
+  // software pipeline: the point of entry e + 1 is fetched before the addition of entry e starts (every table entry
+  // of a lone MSM is used once, so the gathers come from DRAM: ncu showed 10 % of the stall samples on the first use
+  // of the loaded point)
+  uint32_t u = ent[e0];
+  G1Affine p = table[u & 0x7fffffffu];
   for (uint32_t e = e0; e < e1; e++) {
     if (e >= bend) {
       // the run [run_s, bend) of bucket b ends inside this chunk
@@ -379,11 +384,15 @@ __global__ void __launch_bounds__(128, 4) msm_accumulate_flat(const G1Affine* __
       skip = bend - bs >= heavy_thr;
       acc = G1XYZZ::inf();
     }
-    if (!skip) {
-      uint32_t u = ent[e];
-      G1Affine p = table[u & 0x7fffffffu];
-      if (!p.is_inf()) xyzz_add_mixed(acc, p.x, p.y, (u >> 31) != 0);
+    uint32_t un = u;
+    G1Affine pn = p;
+    if (e + 1 < e1) {
+      un = ent[e + 1];
+      pn = table[un & 0x7fffffffu];
     }
+    if (!skip && !p.is_inf()) xyzz_add_mixed(acc, p.x, p.y, (u >> 31) != 0);
+    u = un;
+    p = pn;
   }
   if (!skip) {
     if (run_s == bs && e1 == bend) bk[b] = acc;             // whole bucket ends exactly at the chunk end
