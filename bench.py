@@ -316,7 +316,8 @@ def run_capgpu(args):
 # shapes: (transaction, inputs, outputs, tree height) of the CAP circuit whose domain size the synthetic shape copies
 # (src/utils/mod.rs:137-193)
 CSV_HEADERS = ["TRANSACTION", "N_THREADS", "FUNCTION", "N_INPUTS", "N_OUTPUTS", "TREE_HEIGHT", "DOMAIN_SIZE", "N_CONSTRAINTS", "UTILITY_RATIO(%)",
-               "TRANSFER_NOTE_SIZE (KB)", "PROVING_KEY_SIZE (KB)", "VERIFYING_KEY_SIZE (KB)", "TIME (ms)"]
+               "TRANSFER_NOTE_SIZE (KB)", "PROVING_KEY_SIZE (KB)", "VERIFYING_KEY_SIZE (KB)", "TIME (ms)",
+               "N_GPUS", "ROOFLINE_FRAC"]  # the reference's thirteen columns, then GPU count and roofline fraction
 CSV_SHAPES = {"transfer_2x2": ("transfer_note", 2, 2, 26), "mint": ("mint_note", 1, 2, 26), "freeze_5": ("freeze_note", 5, 5, 26),
               "transfer_3x5": ("transfer_note", 3, 5, 26), "transfer_5x5": ("transfer_note", 5, 5, 26)}
 
@@ -330,19 +331,19 @@ def write_reference_csv(path, line, circ, args):
     rows = []
     threads = line["config"].get("host_threads_per_gpu", args.ctxs)
 
-    def row(name, log_n, ms):
+    def row(name, log_n, ms, frac):
         tx, nin, nout, depth = CSV_SHAPES[name]
         n = 1 << log_n
         pk_kb = (18 * (8 + 32 * n) + 8 + 32 * (n + 3) + 8 * 3 + 32 * (18 + 5) + 96 + 3 * 64) / 1024
         vk_kb = (8 * 3 + 32 * (18 + 5) + 96 + 3 * 64) / 1024
         return [tx, threads, "Gen", nin, nout, depth, n, n, "100.00", "%.3f" % ((13 * 32 + 10 * 32) / 1024), "%.1f" % pk_kb, "%.3f" % vk_kb,
-                "%.4f" % ms]
+                "%.4f" % ms, line["n_gpus"], "" if frac is None else "%.3f" % frac]
 
     per_gpu = line["value"] / max(line["n_gpus"], 1)
-    rows.append(row(args.workload, circ.log_n, 1e3 / per_gpu))
+    rows.append(row(args.workload, circ.log_n, 1e3 / per_gpu, line.get("roofline", {}).get("frac")))
     for name, v in line.get("configs", {}).get("note_shapes", {}).items():
         if name in CSV_SHAPES:
-            rows.append(row(name, int(v["domain"].split("^")[1]), v["ms_per_proof"]))
+            rows.append(row(name, int(v["domain"].split("^")[1]), v["ms_per_proof"], v.get("roofline_frac")))
     with open(path, "w", newline="") as f:
         w = csv.writer(f)
         w.writerow(CSV_HEADERS)

@@ -8,8 +8,13 @@
 // Header-only, C++17, no dependency beyond libcapgpu.so.  Exercised by tests/cpp/replay_fixture.cpp.
 #pragma once
 #include <cstdint>
+#include <functional>
+#include <map>
+#include <memory>
+#include <mutex>
 #include <stdexcept>
 #include <string>
+#include <tuple>
 #include <utility>
 #include <vector>
 
@@ -78,6 +83,27 @@ class ProvingKey {
   capgpu_pk* h_ = nullptr;
   unsigned log_n_ = 0;
   size_t num_inputs_ = 0;
+};
+
+// Device-resident proving keys keyed by (note type, inputs, outputs, tree depth): the GPU-side analogue of the
+// reference's on-disk key cache `transfer_prover_{i}_input_{o}_output_{d}_depth.bin` (src/parameters.rs:485-503).
+// A key is uploaded (deserialised, coset tables and Lagrange commit key derived on the device) once per shape.
+class ProvingKeyCache {
+ public:
+  using Shape = std::tuple<uint64_t, uint64_t, uint64_t, uint64_t>;  // note type (0 transfer, 1 mint, 2 freeze), n_inputs, n_outputs, depth
+  explicit ProvingKeyCache(Context& ctx) : ctx_(ctx) {}
+  // `load` supplies the key's CanonicalSerialize bytes (from disk, or `ProvingKey::serialize` of a freshly preprocessed key)
+  const ProvingKey& get(const Shape& shape, const std::function<std::vector<uint8_t>()>& load) {
+    std::lock_guard<std::mutex> lock(mu_);
+    auto it = keys_.find(shape);
+    if (it == keys_.end()) it = keys_.emplace(shape, std::make_unique<ProvingKey>(ProvingKey::deserialize(ctx_, load()))).first;
+    return *it->second;
+  }
+  size_t size() const { return keys_.size(); }
+ private:
+  Context& ctx_;
+  std::mutex mu_;
+  std::map<Shape, std::unique_ptr<ProvingKey>> keys_;
 };
 
 struct Proof {

@@ -60,7 +60,16 @@ int main(int argc, char** argv) {
   }
   try {
     Context ctx(0);
-    ProvingKey pk = ProvingKey::deserialize(ctx, std::vector<uint8_t>(sec["PK"].begin(), sec["PK"].end()));
+    // keyed like the reference's key files: (note type, inputs, outputs, depth) from the META section
+    uint64_t meta[4];
+    memcpy(meta, sec["META"].data(), 32);
+    ProvingKeyCache cache(ctx);
+    int loads = 0;
+    auto loader = [&] { loads++; return std::vector<uint8_t>(sec["PK"].begin(), sec["PK"].end()); };
+    const ProvingKeyCache::Shape shape{meta[0], meta[1], meta[2], meta[3]};
+    cache.get(shape, loader);
+    const ProvingKey& pk = cache.get(shape, loader);  // second request: served from the device-resident cache
+    if (loads != 1 || cache.size() != 1) throw PlonkError(CAPGPU_ERR_STATE, "proving-key cache reloaded a resident key");
     // WIRES: Vec<Vec<Fr>> -> 5 x n Montgomery limbs
     const std::string& w = sec["WIRES"];
     if (rd64(w, 0) != 5) throw PlonkError(CAPGPU_ERR_ARG, "fixture must hold 5 witness columns");

@@ -14,8 +14,8 @@ def test_reference_csv_layout(tmp_path):
     bench.write_reference_csv(str(path), line, types.SimpleNamespace(log_n=15), types.SimpleNamespace(workload="transfer_2x2", ctxs=4))
     rows = list(csv.reader(open(path)))
     assert rows[0] == ["TRANSACTION", "N_THREADS", "FUNCTION", "N_INPUTS", "N_OUTPUTS", "TREE_HEIGHT", "DOMAIN_SIZE", "N_CONSTRAINTS",
-                       "UTILITY_RATIO(%)", "TRANSFER_NOTE_SIZE (KB)", "PROVING_KEY_SIZE (KB)", "VERIFYING_KEY_SIZE (KB)", "TIME (ms)"]
+                       "UTILITY_RATIO(%)", "TRANSFER_NOTE_SIZE (KB)", "PROVING_KEY_SIZE (KB)", "VERIFYING_KEY_SIZE (KB)", "TIME (ms)", "N_GPUS", "ROOFLINE_FRAC"]
     assert [r[0] for r in rows[1:]] == ["transfer_note", "mint_note", "freeze_note"]
-    assert rows[1][2] == "Gen" and rows[1][6] == "32768" and float(rows[1][-1]) == 2.0  # 1000 proofs/s on 2 GPUs = 2 ms per proof per GPU
-    assert rows[2][6] == "16384" and float(rows[2][-1]) == 1.1
-    assert all(len(r) == 13 for r in rows)
+    assert rows[1][2] == "Gen" and rows[1][6] == "32768" and float(rows[1][12]) == 2.0 and rows[1][13] == "2"  # 1000 proofs/s on 2 GPUs = 2 ms per proof per GPU
+    assert rows[2][6] == "16384" and float(rows[2][12]) == 1.1
+    assert all(len(r) == 15 for r in rows)
