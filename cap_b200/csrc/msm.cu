@@ -697,7 +697,8 @@ void msm_device(capgpu_ctx* ctx, const capgpu_srs* srs, size_t base_off, const F
   // one-wave launches in the low-latency schedule: equal chunks of sorted entries per thread
   const size_t wave_threads = (size_t)ctx->sm_count * 4 * 128;
   const size_t ee = es / parts;  // expected entries of this bucket-range slice
-  const bool flat = latency && msm_tuning().flat && batch * K * lpb <= wave_threads && ee >= msm_tuning().flat_min_entries;
+  // (up to two waves of bucket slots: the five-vector launches of a latency-mode proof at n = 2^15 are 81920 slots)
+  const bool flat = latency && msm_tuning().flat && batch * K * lpb <= 2 * wave_threads && ee >= msm_tuning().flat_min_entries;
 
   {
   ProfScope prof_sort(ctx, PROF_MSM_SORT, (double)batch * W * n);

@@ -22,6 +22,7 @@ TAU = 0x2B7E151628AED2A6ABF7158809CF4F3C762E7160F38B4DA56A784D9045190CFE % field
 log_n, nin = synth.NOTE_SHAPES[args.workload]
 circ = synth.make_circuit(log_n, num_inputs=nin, seed=7)
 ctx = device.Context(0)
+ctx.set_latency_mode(True)  # the single-note schedule (flat accumulation, quad tiles)
 srs = plonk.PlonkKzgSnark.universal_setup(ctx, circ.n + 2, TAU)
 pk = plonk.PlonkKzgSnark.preprocess(ctx, srs, circ)
 wires = plonk.wire_values(circ)
