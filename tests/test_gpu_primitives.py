@@ -291,6 +291,22 @@ def test_msm_bucket_range_slices_sum_to_the_msm(ctx, log_n, parts):
             _lib.check(ctx.lib.capgpu_g1_sum_xyzz_dev(ctx.h, c_void_p(xy.data_ptr()), parts, c_void_p(total2.data_ptr())), ctx.h)
             ctx.sync()
             assert np.array_equal(total2.cpu().numpy().view(np.uint64), want)
+            # fused exchange on one GPU: every slice stores its sum into "its" slot of a (here local) buffer and releases
+            # the slot's flag; the fold waits on all flags (what each GPU of a split does with its peers' slices)
+            import ctypes
+            buf = torch.zeros(16 * parts + 16 * ((parts + 15) // 16), dtype=torch.int64, device="cuda")
+            flags_off = 16 * parts * 8
+            for epoch in (1, 2):
+                for p in range(parts):
+                    slots = (ctypes.c_void_p * 1)(buf.data_ptr() + 128 * p)
+                    flags = (ctypes.c_void_p * 1)(buf.data_ptr() + flags_off + 8 * p)
+                    _lib.check(ctx.lib.capgpu_msm_g1_dev_part_peer(ctx.h, srs.h, 0, c_void_p(d.data_ptr()), n, 0, p, parts, slots, flags, 1, epoch), ctx.h)
+                total3 = torch.zeros(8, dtype=torch.int64, device="cuda")
+                _lib.check(ctx.lib.capgpu_g1_sum_xyzz_wait_dev(ctx.h, c_void_p(buf.data_ptr()), c_void_p(buf.data_ptr() + flags_off), 8, parts, epoch,
+                                                               c_void_p(total3.data_ptr())), ctx.h)
+                ctx.sync()
+                assert np.array_equal(total3.cpu().numpy().view(np.uint64), want)
+            assert ctx.lib.capgpu_msm_g1_dev_part_peer(ctx.h, srs.h, 0, c_void_p(d.data_ptr()), n, 0, 0, parts, None, None, 1, 1) == -2
         else:
             assert rcs == [-2] * parts  # fewer than 512 buckets per slice: affine slices only
     assert ctx.lib.capgpu_msm_g1_dev_part(ctx.h, srs.h, 0, c_void_p(d.data_ptr()), n, 0, 3, 3, c_void_p(total.data_ptr())) == -2
