@@ -318,12 +318,42 @@ __device__ __forceinline__ void ntt_phase_butterflies(Fr (&x)[8], uint32_t t, co
   }
 }
 
+// First phase of a transform whose input is zero beyond the first stride (the 8n-point quotient-domain transforms read
+// n + 3 coefficients: in the column pass only slot 0 of a thread is loaded).  Butterflies with a zero partner are
+// copies, (u, 0) -> (u, u * tw): 1 + 2 + 4 products for the three stages instead of 12, no additions.  Same twiddle
+// indices as ntt_phase_butterflies<LOG_T, 0, 3>, so the result is identical.
+template <int LOG_T>
+__device__ __forceinline__ void ntt_phase0_slot0_only(Fr (&x)[8], uint32_t t, const Fr* __restrict__ tw) {
+  constexpr int LOG_STRIDE = LOG_T - 3;
+  const uint32_t lo = t & ((1u << LOG_STRIDE) - 1u);
+  // stage l (half = 4, 2, 1; log_m = LOG_STRIDE + 2 - l): every butterfly here has i & (half - 1) == 0, so k = lo
+  x[4] = ntt_mul(x[0], tw[lo << (9 - (LOG_STRIDE + 2))]);
+  {
+    const Fr w = tw[lo << (9 - (LOG_STRIDE + 1))];
+    x[2] = ntt_mul(x[0], w);
+    x[6] = ntt_mul(x[4], w);
+  }
+  {
+    const Fr w = tw[lo << (9 - LOG_STRIDE)];
+    x[1] = ntt_mul(x[0], w);
+    x[3] = ntt_mul(x[2], w);
+    x[5] = ntt_mul(x[4], w);
+    x[7] = ntt_mul(x[6], w);
+  }
+}
+
 template <int LOG_T, int PH>
 struct NttPhaseRunner {
-  static __device__ __forceinline__ void run(Fr (&x)[8], uint32_t t, const Fr* __restrict__ tw, uint32_t* tile, uint32_t plane) {
+  static __device__ __forceinline__ void run(Fr (&x)[8], uint32_t t, const Fr* __restrict__ tw, uint32_t* tile, uint32_t plane,
+                                             bool slot0_only = false) {
     constexpr int S = ntt_phase_start(LOG_T, PH);
     constexpr int RR = ntt_phase_stages(LOG_T, PH);
-    ntt_phase_butterflies<LOG_T, S, RR>(x, t, tw);
+    if constexpr (PH == 0 && RR == 3) {
+      if (slot0_only) ntt_phase0_slot0_only<LOG_T>(x, t, tw);
+      else ntt_phase_butterflies<LOG_T, S, RR>(x, t, tw);
+    } else {
+      ntt_phase_butterflies<LOG_T, S, RR>(x, t, tw);
+    }
     if constexpr (PH + 1 < ntt_num_phases(LOG_T)) {
       constexpr int S2 = ntt_phase_start(LOG_T, PH + 1);
       constexpr int RR2 = ntt_phase_stages(LOG_T, PH + 1);
@@ -354,6 +384,7 @@ __global__ void __launch_bounds__(256, 2) ntt_reg_kernel(NttPass P) {
 
   Fr x[8];
   constexpr int R0 = ntt_phase_stages(LOG_T, 0);
+  bool upper_loaded = false;  // any of slots 1..7 inside the input
 #pragma unroll
   for (int e = 0; e < 8; e++) {
     const uint32_t pos = ntt_slot_pos<LOG_T, 0, R0>(t, e);
@@ -361,11 +392,13 @@ __global__ void __launch_bounds__(256, 2) ntt_reg_kernel(NttPass P) {
     if (idx < P.src_len) {
       x[e] = src[idx];
       if (P.pre) x[e] = ntt_mul(x[e], P.pre[pos]);
+      if (e > 0) upper_loaded = true;
     } else {
       x[e] = Fr::zero();
     }
   }
-  NttPhaseRunner<LOG_T, 0>::run(x, t, P.tw, tile, plane);
+  // zero-extended inputs (src_len <= 1/8 of the columns' length): the first three stages only copy and scale slot 0
+  NttPhaseRunner<LOG_T, 0>::run(x, t, P.tw, tile, plane, R0 == 3 && !upper_loaded);
   constexpr int LAST = ntt_num_phases(LOG_T) - 1;
   constexpr int SL = ntt_phase_start(LOG_T, LAST), RL = ntt_phase_stages(LOG_T, LAST);
 #pragma unroll
