@@ -84,9 +84,16 @@ __host__ __device__ __forceinline__ FpN<PR> fp_neg(const FpN<PR>& a) { return a.
 template <class PR>
 __host__ __device__ __forceinline__ FpN<PR> fp_dbl(const FpN<PR>& a) { return fp_add(a, a); }
 
-// CIOS Montgomery product (Koc et al.): row of a * b_i, then one reduction step, N times
+// CIOS Montgomery product (Koc et al.): row of a * b_i, then one reduction step, N times.  Out of line on the
+// device (one copy per field instead of one per call site: the 12-limb product is ~600 instructions and the
+// group law calls it 10-14 times; keeps msm_curve.cu's compile time and instruction footprint small).
+#ifdef __CUDACC__
+#define CAPGPU_FPN_NOINLINE __noinline__
+#else
+#define CAPGPU_FPN_NOINLINE
+#endif
 template <class PR>
-__host__ __device__ inline FpN<PR> fp_mul(const FpN<PR>& a, const FpN<PR>& b) {
+__host__ __device__ CAPGPU_FPN_NOINLINE FpN<PR> fp_mul(const FpN<PR>& a, const FpN<PR>& b) {
   constexpr int N = PR::N;
   uint32_t t[N + 2];
 #pragma unroll
@@ -138,7 +145,7 @@ __host__ __device__ inline FpN<PR> fp_inv_fermat(const FpN<PR>& a) {
 // Binary GCD in batched rounds, as fp.cuh's fp_inv (same invariants: a R^2 = u y, b R^2 = v y mod p), over N limbs:
 // ceil((2 BITS - 1) / 30) rounds of 30 steps on 62-bit approximations.  inv(0) = 0.
 template <class PR>
-__host__ __device__ inline FpN<PR> fp_inv(const FpN<PR>& y) {
+__host__ __device__ CAPGPU_FPN_NOINLINE FpN<PR> fp_inv(const FpN<PR>& y) {
   constexpr int N = PR::N;
   if (y.is_zero()) return y;
   uint32_t a[N], b[N], u[N], v[N];
