@@ -116,7 +116,7 @@ def test_msm_golden_and_upload_path(ctx, golden):
     srs.close()
 
 
-@pytest.mark.parametrize("window_bits", [0, 2, 5, 11, 16])
+@pytest.mark.parametrize("window_bits", [0, 2, 5, 10, 11, 13, 16])
 def test_msm_edge_cases(ctx, window_bits):
     n = 300
     srs = device.Srs(ctx, tau_mont=field.fr_to_mont_array([TAU])[0], size=n, window_bits=window_bits)
