@@ -28,6 +28,10 @@ static __device__ __constant__ uint32_t kRoot28[8] = {0x80d13d9cu, 0x636e7355u, 
 static __device__ __constant__ uint32_t kRoot28Inv[8] = {0x584bb683u, 0x89bcc016u, 0x0164a50cu, 0xe8d9887fu, 0x795eda3du, 0x755e95cbu, 0x1323b130u, 0x0f572b87u};
 static __device__ __constant__ uint32_t kGen[8] = {0x9fffffe6u, 0x1b0d0ef9u, 0xa32a913fu, 0xeaba68a3u, 0xd8dd0689u, 0x47d8eb76u, 0x20f5bbc3u, 0x15d00855u};
 static __device__ __constant__ uint32_t kGenInv[8] = {0x09999999u, 0xd7453974u, 0x83c3efa8u, 0xb4ada7d4u, 0xe57f3161u, 0xc49ca2f8u, 0xac156cb3u, 0x162a3754u};
+// rho = 5^((r-1) / (3 * 2^28)): rho^3 = kRoot28; rho^(2^(28-L)) has order 3 * 2^L (the 3-coset quotient domain below)
+static __device__ __constant__ uint32_t kRho28[8] = {0x938bb649u, 0x70f4a36du, 0xf4178187u, 0xb81a7492u, 0x69f2125eu, 0x22e5d044u, 0x6fdced23u, 0x0a0b8416u};
+static __device__ __constant__ uint32_t kRho28Inv[8] = {0x2be48eafu, 0x3b5f7128u, 0xd733e268u, 0x74742b2bu, 0xe4d48d21u, 0x5633d495u, 0x2da8cb77u, 0x23355141u};
+static __device__ __constant__ uint32_t kInv3[8] = {0x15555554u, 0xfad2b890u, 0x5db369e8u, 0x75101f9fu, 0x53538a2eu, 0xb4ea4db7u, 0xd3bdd51du, 0x14cf9766u};
 static __device__ __constant__ uint32_t kInv2[8] = {0x1ffffffeu, 0x783c14d8u, 0x0c8d1eddu, 0xaf982f6fu, 0xfcfd4f45u, 0x8f5f7492u, 0x3d9cbfacu, 0x1f37631au};
 
 struct NttVariant {
@@ -42,6 +46,7 @@ struct NttDomain {
   size_t n = 0;
   Fr* tile_tw[2] = {nullptr, nullptr};  // w_1024^k and w_1024^-k, k < 512
   NttVariant var[2][2];                 // [inverse][coset]
+  NttVariant var3[2];                   // [inverse]: the three cosets g rho^k H of the 3 * 2^log_n domain, tables [3][..]
   Fr* omega_pows = nullptr;             // w_n^j, j < n (built on demand)
 };
 
@@ -69,7 +74,17 @@ enum TableKind {
   TBL_POST = 5,       // [g^-i] / n
 };
 
-__global__ void ntt_build_table(Fr* out, size_t count, int kind, unsigned log_n, unsigned log_c, int inverse, int coset) {
+// coset shift of a table: none (coset 0), g (coset 1), or g * rho^k with rho of order 3 * 2^log_n (coset 2); `inv` gives its inverse
+__device__ inline Fr ntt_shift(int coset, int k, unsigned log_n, bool inv) {
+  Fr s = load_const(inv ? kGenInv : kGen);
+  if (coset == 2 && k > 0) {
+    Fr rho = sqr_times(load_const(inv ? kRho28Inv : kRho28), 28 - log_n);
+    s = fp_mul(s, k == 1 ? rho : fp_sqr(rho));
+  }
+  return s;
+}
+
+__global__ void ntt_build_table(Fr* out, size_t count, int kind, unsigned log_n, unsigned log_c, int inverse, int coset, int k) {
   size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= count) return;
   Fr root = load_const(inverse ? kRoot28Inv : kRoot28);
@@ -91,18 +106,19 @@ __global__ void ntt_build_table(Fr* out, size_t count, int kind, unsigned log_n,
       uint64_t j2 = idx & c_mask, i1 = idx >> log_c;
       Fr w = sqr_times(root, 28 - log_n);
       v = fp_pow_u64(w, j2 * i1);
-      if (coset && !inverse) v = fp_mul(v, fp_pow_u64(load_const(kGen), j2));
+      if (coset && !inverse) v = fp_mul(v, fp_pow_u64(ntt_shift(coset, k, log_n, false), j2));
       if (inverse && !coset) v = fp_mul(v, fp_pow_u64(load_const(kInv2), log_n));
       break;
     }
     case TBL_PRE: {
-      Fr gc = sqr_times(load_const(kGen), log_c);
+      Fr gc = sqr_times(ntt_shift(coset, k, log_n, false), log_c);
       v = fp_pow_u64(gc, idx);
       break;
     }
     case TBL_POST: {
       v = fp_pow_u64(load_const(kInv2), log_n);
-      if (coset) v = fp_mul(v, fp_pow_u64(load_const(kGenInv), idx));
+      if (coset) v = fp_mul(v, fp_pow_u64(ntt_shift(coset, k, log_n, true), idx));
+      if (coset == 2) v = fp_mul(v, load_const(kInv3));  // the 1/3 of the radix-3 recombination
       break;
     }
     default:
@@ -112,10 +128,13 @@ __global__ void ntt_build_table(Fr* out, size_t count, int kind, unsigned log_n,
 }
 
 static Fr* build_table(capgpu_ctx* ctx, size_t count, int kind, unsigned log_n, unsigned log_c, int inverse, int coset) {
+  const int copies = coset == 2 ? 3 : 1;  // [3][count]: one table per coset g rho^k H
   Fr* p = nullptr;
-  CAPGPU_CUDA(cudaMalloc(&p, count * sizeof(Fr)));
-  ntt_build_table<<<ceil_div(count, 128), 128, 0, ctx->stream>>>(p, count, kind, log_n, log_c, inverse, coset);
-  CAPGPU_LAUNCH_CHECK(ctx);
+  CAPGPU_CUDA(cudaMalloc(&p, copies * count * sizeof(Fr)));
+  for (int k = 0; k < copies; k++) {
+    ntt_build_table<<<ceil_div(count, 128), 128, 0, ctx->stream>>>(p + (size_t)k * count, count, kind, log_n, log_c, inverse, coset, k);
+    CAPGPU_LAUNCH_CHECK(ctx);
+  }
   return p;
 }
 
@@ -134,12 +153,13 @@ NttDomain* get_domain(capgpu_ctx* ctx, unsigned log_n) {
   return d;
 }
 
-static void build_variant(capgpu_ctx* ctx, NttDomain* d, bool inverse, bool coset) {
-  NttVariant& v = d->var[inverse][coset];
+static void build_variant(capgpu_ctx* ctx, NttDomain* d, bool inverse, int coset) {
+  NttVariant& v = coset == 2 ? d->var3[inverse] : d->var[inverse][coset];
   if (v.built) return;
   bool two_pass = d->log_c > 0;
-  if (two_pass) v.mid = build_table(ctx, d->n, TBL_MID, d->log_n, d->log_c, inverse, coset);
-  if (coset && !inverse) v.pre = build_table(ctx, (size_t)1 << d->log_r, TBL_PRE, d->log_n, d->log_c, 0, 1);
+  // the inverse transform's mid table carries no shift: one copy serves the three cosets
+  if (two_pass) v.mid = build_table(ctx, d->n, TBL_MID, d->log_n, d->log_c, inverse, inverse && coset == 2 ? 1 : coset);
+  if (coset && !inverse) v.pre = build_table(ctx, (size_t)1 << d->log_r, TBL_PRE, d->log_n, d->log_c, 0, coset);
   if (inverse && (coset || !two_pass)) v.post = build_table(ctx, d->n, TBL_POST, d->log_n, d->log_c, 1, coset);
   v.built = true;
 }
@@ -154,10 +174,11 @@ void destroy_domain(NttDomain* d) {
   if (!d) return;
   for (int i = 0; i < 2; i++) {
     if (d->tile_tw[i]) cudaFree(d->tile_tw[i]);
-    for (int c = 0; c < 2; c++) {
-      if (d->var[i][c].pre) cudaFree(d->var[i][c].pre);
-      if (d->var[i][c].mid) cudaFree(d->var[i][c].mid);
-      if (d->var[i][c].post) cudaFree(d->var[i][c].post);
+    for (int c = 0; c < 3; c++) {
+      NttVariant& v = c == 2 ? d->var3[i] : d->var[i][c];
+      if (v.pre) cudaFree(v.pre);
+      if (v.mid) cudaFree(v.mid);
+      if (v.post) cudaFree(v.post);
     }
   }
   if (d->omega_pows) cudaFree(d->omega_pows);
@@ -177,7 +198,18 @@ struct NttPass {
   const Fr* pre;
   const Fr* post;
   const Fr* tw;
+  // 3-coset transforms: row y of the batch reads input y / src_div and uses table copy y % tbl_mod
+  uint32_t src_div = 1, tbl_mod = 1;
+  uint32_t pre_kstride = 0, post_kstride = 0;
 };
+
+// input row and table copy of batch row y
+__device__ __forceinline__ void ntt_row_setup(const NttPass& P, uint32_t y, const Fr*& src, const Fr*& pre, const Fr*& post) {
+  src = P.src + (size_t)(P.src_div > 1 ? y / P.src_div : y) * P.src_stride;
+  const uint32_t k = P.tbl_mod > 1 ? y % P.tbl_mod : 0;
+  pre = P.pre ? P.pre + (size_t)k * P.pre_kstride : nullptr;
+  post = P.post ? P.post + (size_t)k * P.post_kstride : nullptr;
+}
 
 __device__ __forceinline__ Fr smem_load(const uint32_t* s, uint32_t plane, uint32_t e) {
   Fr r;
@@ -197,7 +229,8 @@ __global__ void __launch_bounds__(512) ntt_tile_kernel(NttPass P) {
   const uint32_t TS = T + PAD;
   const uint32_t plane = G * TS;
   const uint32_t gbase = blockIdx.x * G;
-  const Fr* src = P.src + (size_t)blockIdx.y * P.src_stride;
+  const Fr *src, *pre, *post;
+  ntt_row_setup(P, blockIdx.y, src, pre, post);
   Fr* dst = P.dst + (size_t)blockIdx.y * P.dst_stride;
 
   for (uint32_t ld = threadIdx.x; ld < E; ld += blockDim.x) {
@@ -208,7 +241,7 @@ __global__ void __launch_bounds__(512) ntt_tile_kernel(NttPass P) {
     Fr x;
     if (idx < P.src_len) {
       x = src[idx];
-      if (P.pre) x = fp_mul(x, P.pre[p]);
+      if (pre) x = fp_mul(x, pre[p]);
     } else {
       x = Fr::zero();
     }
@@ -240,7 +273,7 @@ __global__ void __launch_bounds__(512) ntt_tile_kernel(NttPass P) {
     uint32_t p = P.log_t ? (__brev(q) >> (32 - P.log_t)) : 0;
     Fr x = smem_load(smem, plane, g * TS + p);
     uint32_t oidx = q * P.out_q_stride + (gbase + g) * P.out_g_stride;
-    if (P.post) x = fp_mul(x, P.post[oidx]);
+    if (post) x = fp_mul(x, post[oidx]);
     dst[oidx] = x;
   }
 }
@@ -378,7 +411,8 @@ __global__ void __launch_bounds__(256, 2) ntt_reg_kernel(NttPass P) {
   if (P.in_p_stride == 1) { g = threadIdx.x / TPT; t = threadIdx.x % TPT; }  // rows: lanes walk positions
   else { g = threadIdx.x & (G - 1); t = threadIdx.x >> P.log_g; }           // columns: lanes walk adjacent columns
   const uint32_t gcol = blockIdx.x * G + g;
-  const Fr* src = P.src + (size_t)blockIdx.y * P.src_stride;
+  const Fr *src, *pre, *post;
+  ntt_row_setup(P, blockIdx.y, src, pre, post);
   Fr* dst = P.dst + (size_t)blockIdx.y * P.dst_stride;
   uint32_t* tile = smem + g * TP;
 
@@ -391,7 +425,7 @@ __global__ void __launch_bounds__(256, 2) ntt_reg_kernel(NttPass P) {
     const uint32_t idx = pos * P.in_p_stride + gcol * P.in_g_stride;
     if (idx < P.src_len) {
       x[e] = src[idx];
-      if (P.pre) x[e] = ntt_mul(x[e], P.pre[pos]);
+      if (pre) x[e] = ntt_mul(x[e], pre[pos]);
       if (e > 0) upper_loaded = true;
     } else {
       x[e] = Fr::zero();
@@ -407,7 +441,7 @@ __global__ void __launch_bounds__(256, 2) ntt_reg_kernel(NttPass P) {
     const uint32_t q = __brev(pos) >> (32 - LOG_T);
     const uint32_t oidx = q * P.out_q_stride + gcol * P.out_g_stride;
     Fr v = x[e];
-    if (P.post) v = ntt_mul(v, P.post[oidx]);
+    if (post) v = ntt_mul(v, post[oidx]);
     dst[oidx] = v;
   }
 }
@@ -455,40 +489,95 @@ static void launch_pass(capgpu_ctx* ctx, const NttPass& p, size_t n, size_t batc
   CAPGPU_LAUNCH_CHECK(ctx);
 }
 
-void ntt_device(capgpu_ctx* ctx, unsigned log_n, const Fr* src, size_t src_len, size_t src_stride, Fr* dst,
-                size_t dst_stride, Fr* tmp, size_t batch, bool inverse, bool coset) {
+// `cosets` = 1: `batch` transforms (plain or on the coset g H).  `cosets` = 3: every input is transformed on the three cosets
+// g rho^k H (k = 0, 1, 2) of the 3 * 2^log_n-point domain; the batch rows are (input, k), output row stride dst_stride.
+static void ntt_run(capgpu_ctx* ctx, unsigned log_n, const Fr* src, size_t src_len, size_t src_stride, Fr* dst, size_t dst_stride, Fr* tmp,
+                    size_t batch, bool inverse, int coset) {
   NttDomain* d = get_domain(ctx, log_n);
   build_variant(ctx, d, inverse, coset);
-  const NttVariant& v = d->var[inverse][coset];
+  const NttVariant& v = coset == 2 ? d->var3[inverse] : d->var[inverse][coset];
   CAPGPU_REQUIRE(src_len <= d->n, "NTT input longer than the domain");
   if (batch == 0) return;
+  const uint32_t R = 1u << d->log_r, C = 1u << d->log_c;
+  const uint32_t tbl_mod = coset == 2 ? 3 : 1;
+  const uint32_t src_div = coset == 2 && !inverse ? 3 : 1;  // forward: the three cosets share one input
+  if (coset == 2) batch *= 3;
   NttPass p;
   p.tw = d->tile_tw[inverse ? 1 : 0];
   p.src_len = (uint32_t)src_len;
+  p.tbl_mod = tbl_mod;
   if (d->log_c == 0) {
     p.src = src; p.dst = dst; p.src_stride = src_stride; p.dst_stride = dst_stride;
+    p.src_div = src_div;
     p.log_t = log_n; p.log_g = 0;
     p.in_p_stride = 1; p.in_g_stride = 0; p.out_q_stride = 1; p.out_g_stride = 0;
     p.pre = v.pre; p.post = v.post;
+    p.pre_kstride = R; p.post_kstride = (uint32_t)d->n;
     launch_pass(ctx, p, d->n, batch);
     return;
   }
-  const uint32_t R = 1u << d->log_r, C = 1u << d->log_c;
   // pass 1: columns
   p.src = src; p.dst = tmp; p.src_stride = src_stride; p.dst_stride = d->n;
+  p.src_div = src_div;
   p.log_t = d->log_r; p.log_g = 10 - d->log_r;
   if ((1u << p.log_g) > C) p.log_g = d->log_c;
   p.in_p_stride = C; p.in_g_stride = 1; p.out_q_stride = C; p.out_g_stride = 1;
   p.pre = v.pre; p.post = v.mid;
+  p.pre_kstride = R; p.post_kstride = inverse ? 0u : (uint32_t)d->n;
   launch_pass(ctx, p, d->n, batch);
   // pass 2: rows
   p.src = tmp; p.dst = dst; p.src_stride = d->n; p.dst_stride = dst_stride;
+  p.src_div = 1;
   p.src_len = (uint32_t)d->n;
   p.log_t = d->log_c; p.log_g = 10 - d->log_c;
   if ((1u << p.log_g) > R) p.log_g = d->log_r;
   p.in_p_stride = 1; p.in_g_stride = C; p.out_q_stride = R; p.out_g_stride = 1;
   p.pre = nullptr; p.post = v.post;
+  p.pre_kstride = 0; p.post_kstride = (uint32_t)d->n;
   launch_pass(ctx, p, d->n, batch);
+}
+
+void ntt_device(capgpu_ctx* ctx, unsigned log_n, const Fr* src, size_t src_len, size_t src_stride, Fr* dst,
+                size_t dst_stride, Fr* tmp, size_t batch, bool inverse, bool coset) {
+  ntt_run(ctx, log_n, src, src_len, src_stride, dst, dst_stride, tmp, batch, inverse, coset ? 1 : 0);
+}
+
+// ------------------------------------------------------------------------------------------
+// The 3 * 2^L-point quotient domain D = g <rho>, rho of order 3N (N = 2^L), as the three cosets s_k H_N, s_k = g rho^k:
+// point (k, i) = s_k w_N^i sits at index k * N + i.  A polynomial of degree < 3N is evaluated on D by three N-point coset
+// transforms of its (zero-extended) coefficients, and recovered from its values by three inverse coset transforms
+//     u_k(X) = t(X) mod (X^N - c_k),  c_k = s_k^N = g^N zeta^k,  zeta = rho^N (a primitive cube root of unity),
+// followed by the radix-3 step  t_{j + aN} = (1/3) g^(-aN) sum_k zeta^(-ak) u_k[j].  The PLONK quotient has degree 5n + 7,
+// so N = 2n gives 6n points instead of the 8n of the next power of two: 25 % fewer point-wise evaluations and 2n-point
+// transforms (16 butterfly stages at n = 2^15 instead of 18).  The result is the same polynomial, coefficient for coefficient.
+// ------------------------------------------------------------------------------------------
+void ntt3_forward(capgpu_ctx* ctx, unsigned log_n, const Fr* src, size_t src_len, size_t src_stride, Fr* dst, Fr* tmp, size_t batch) {
+  ntt_run(ctx, log_n, src, src_len, src_stride, dst, (size_t)1 << log_n, tmp, batch, false, 2);
+}
+
+// u_k in rows (b, k) of `t` -> coefficients t_0 .. t_{3N-1} in place; z1 = zeta^-1, gi1 = g^-N, gi2 = g^-2N (the 1/3 is in the
+// inverse transforms' post table).  With zeta^-2 = -1 - zeta^-1 the step costs two products plus the two scalings per j.
+__global__ void ntt3_recombine_kernel(Fr* t, uint32_t N, Fr z1, Fr gi1, Fr gi2) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= N) return;
+  Fr* row = t + (size_t)blockIdx.y * 3 * N;
+  const Fr u0 = row[j], u1 = row[N + j], u2 = row[2 * (size_t)N + j];
+  const Fr p1 = fp_mul(z1, u1), q1 = fp_mul(z1, u2);
+  // a = 1: u0 + z1 u1 + z2 u2 = u0 + p1 - u2 - q1;   a = 2: u0 + z2 u1 + z1 u2 = u0 - u1 - p1 + q1
+  const Fr a1 = fp_sub(fp_add(u0, p1), fp_add(u2, q1));
+  const Fr a2 = fp_sub(fp_add(u0, q1), fp_add(u1, p1));
+  row[j] = fp_add(fp_add(u0, u1), u2);
+  row[N + j] = fp_mul(a1, gi1);
+  row[2 * (size_t)N + j] = fp_mul(a2, gi2);
+}
+
+void ntt3_inverse(capgpu_ctx* ctx, unsigned log_n, Fr* t, Fr* tmp, size_t batch, const Fr& z1, const Fr& gi1, const Fr& gi2) {
+  const size_t N = (size_t)1 << log_n;
+  ntt_run(ctx, log_n, t, N, N, t, N, tmp, batch, true, 2);
+  if (batch == 0) return;
+  ProfScope prof(ctx, PROF_NTT, (double)batch * 2.0 * (double)N);
+  ntt3_recombine_kernel<<<dim3((unsigned)ceil_div(N, 128), (unsigned)batch), 128, 0, ctx->stream>>>(t, (uint32_t)N, z1, gi1, gi2);
+  CAPGPU_LAUNCH_CHECK(ctx);
 }
 
 }  // namespace capgpu

@@ -1,6 +1,6 @@
 // Polynomial-side kernels of the TurboPlonk prover (everything between the NTTs and MSMs):
 // blinding, permutation grand product with batch inversion, point-wise quotient evaluation on
-// the 8n coset, quotient splitting, Horner evaluation, linearisation / batching, division by
+// the quotient domain (8n coset or 3 x 2n cosets), quotient splitting, Horner evaluation, linearisation / batching, division by
 // (X - z).  Each replaces a CPU loop of jf-plonk 0.1.2 `Prover` / jf-relation 0.1.2
 // `PlonkCircuit` behind /root/reference/src/proof/transfer.rs:181 (names cited per kernel).
 #include "poly.cuh"
@@ -159,7 +159,7 @@ void grand_product(capgpu_ctx* ctx, const Fr* wires, size_t wstride, const Fr* s
 }
 
 // ------------------------------------------------------------------------------------------
-// Quotient evaluation on the 8n coset (jf-plonk Prover::compute_quotient_polynomial's point-wise
+// Quotient evaluation on the quotient domain (QuotDomain, poly.cuh; jf-plonk Prover::compute_quotient_polynomial's point-wise
 // closure: compute_quotient_circuit_contribution + compute_quotient_copy_constraint_contribution):
 //   t(x) = (t_circ + alpha*[z(x) prod(w_i + beta k_i x + gamma) - z(wx) prod(w_i + beta sigma_i + gamma)]) / Z_H(x)
 //          + alpha^2 (z(x) - 1) / (n (x - 1))
@@ -174,9 +174,10 @@ __device__ __forceinline__ Fr pow5(const Fr& w) {
 template <int MINB>
 __global__ void __launch_bounds__(128, MINB) quotient_kernel(const Fr* __restrict__ coset /*7 x m: w0..w4, pi, z*/, const Fr* __restrict__ sel /*13 x m*/,
                                                        const Fr* __restrict__ sig /*5 x m*/, const Fr* __restrict__ xs /*m*/,
-                                                       const Fr* __restrict__ l1inv /*m*/, const Fr* __restrict__ zh_inv /*8*/, size_t m,
+                                                       const Fr* __restrict__ l1inv /*m*/, const Fr* __restrict__ zh_inv /*cosets x step*/, QuotDomain qd,
                                                        int G, const QuotArgs* __restrict__ argv, Fr* out) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t m = qd.m;
   if (i >= m) return;
   const int g = blockIdx.y;
   const QuotArgs& a = argv[g];
@@ -199,8 +200,9 @@ __global__ void __launch_bounds__(128, MINB) quotient_kernel(const Fr* __restric
   acc = fp_add(acc, fp_mul_sub(sel[12 * m + i], fp_mul(fp_mul(w01, w23), w[4]), sel[10 * m + i], w[4]));
   // permutation part
   Fr z = coset[6 * cm + i];
-  size_t inext = i + 8;
-  if (inext >= m) inext -= m;
+  const size_t isub = i & (qd.sub - 1);
+  size_t inext = i + qd.step;  // w_n x, inside the same coset
+  if (isub + qd.step >= qd.sub) inext -= qd.sub;
   Fr zn = coset[6 * cm + inext];
   Fr bx = fp_mul(a.beta, xs[i]);
   Fr r1 = z, r2 = zn;
@@ -212,34 +214,37 @@ __global__ void __launch_bounds__(128, MINB) quotient_kernel(const Fr* __restric
     r2 = fp_mul(r2, fp_add(wg, fp_mul(a.beta, sig[(size_t)j * m + i])));
   }
   acc = fp_add(acc, fp_mul(a.alpha, fp_sub(r1, r2)));
-  // acc / Z_H(x) + alpha^2 (z - 1) / (n (x - 1)); zh_inv: device table 1 / ((g w_m^i)^n - 1), period 8
-  out[i] = fp_mul_add(acc, zh_inv[i & 7], fp_mul(a.alpha2, fp_sub(z, Fr::one())), l1inv[i]);
+  // acc / Z_H(x) + alpha^2 (z - 1) / (n (x - 1)); zh_inv: device table 1 / ((s_k w_sub^i)^n - 1), period `step` in i
+  out[i] = fp_mul_add(acc, zh_inv[(i >> qd.log_sub) * qd.step + (isub & (qd.step - 1))], fp_mul(a.alpha2, fp_sub(z, Fr::one())), l1inv[i]);
 }
 
 void quotient_evals(capgpu_ctx* ctx, const Fr* coset, const Fr* sel, const Fr* sig, const Fr* xs, const Fr* l1inv, const Fr* zh_inv,
-                    size_t m, int G, const QuotArgs* args, Fr* out) {
+                    const QuotDomain& qd, int G, const QuotArgs* args, Fr* out) {
+  const size_t m = qd.m;
   ProfScope prof(ctx, PROF_QUOTIENT, (double)m * G);
   // resident CTAs per SM (register cap): 2 = 176 registers (ncu: 2 warps per scheduler, multiplier busy 65 %; 507 proofs/s), 3 / 4 (525 / 530 proofs/s) trade
   // a few spills for occupancy; CAPGPU_QUOT_MINB selects for A/B runs
   static const int minb = [] { const char* e = getenv("CAPGPU_QUOT_MINB"); int v = e ? atoi(e) : 4; return v < 2 ? 2 : (v > 4 ? 4 : v); }();
   const dim3 grid(ceil_div(m, 128), G);
-  if (minb == 2) quotient_kernel<2><<<grid, 128, 0, ctx->stream>>>(coset, sel, sig, xs, l1inv, zh_inv, m, G, args, out);
-  else if (minb == 3) quotient_kernel<3><<<grid, 128, 0, ctx->stream>>>(coset, sel, sig, xs, l1inv, zh_inv, m, G, args, out);
-  else quotient_kernel<4><<<grid, 128, 0, ctx->stream>>>(coset, sel, sig, xs, l1inv, zh_inv, m, G, args, out);
+  if (minb == 2) quotient_kernel<2><<<grid, 128, 0, ctx->stream>>>(coset, sel, sig, xs, l1inv, zh_inv, qd, G, args, out);
+  else if (minb == 3) quotient_kernel<3><<<grid, 128, 0, ctx->stream>>>(coset, sel, sig, xs, l1inv, zh_inv, qd, G, args, out);
+  else quotient_kernel<4><<<grid, 128, 0, ctx->stream>>>(coset, sel, sig, xs, l1inv, zh_inv, qd, G, args, out);
   CAPGPU_LAUNCH_CHECK(ctx);
 }
 
-// pk tables: xs[i] = g * w_m^i, l1inv[i] = 1 / (n * (xs[i] - 1))
-__global__ void coset_tables_kernel(const Fr* __restrict__ omega_m, size_t m, Fr gen, Fr n_mont, Fr* xs, Fr* l1inv) {
+// pk tables: xs[k * sub + i] = s_k * w_sub^i, l1inv = 1 / (n * (xs - 1))
+__global__ void coset_tables_kernel(const Fr* __restrict__ omega_sub, QuotDomain qd, CosetShifts shifts, Fr n_mont, Fr* xs, Fr* l1inv) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= m) return;
-  Fr x = fp_mul(gen, omega_m[i]);
+  if (i >= qd.m) return;
+  const uint32_t k = (uint32_t)(i >> qd.log_sub);
+  const Fr s = k == 0 ? shifts.s[0] : (k == 1 ? shifts.s[1] : shifts.s[2]);
+  Fr x = fp_mul(s, omega_sub[i & (qd.sub - 1)]);
   xs[i] = x;
   l1inv[i] = fp_inv(fp_mul(n_mont, fp_sub(x, Fr::one())));
 }
 
-void coset_tables(capgpu_ctx* ctx, const Fr* omega_m, size_t m, const Fr& gen, const Fr& n_mont, Fr* xs, Fr* l1inv) {
-  coset_tables_kernel<<<ceil_div(m, 128), 128, 0, ctx->stream>>>(omega_m, m, gen, n_mont, xs, l1inv);
+void coset_tables(capgpu_ctx* ctx, const Fr* omega_sub, const QuotDomain& qd, const CosetShifts& shifts, const Fr& n_mont, Fr* xs, Fr* l1inv) {
+  coset_tables_kernel<<<ceil_div(qd.m, 128), 128, 0, ctx->stream>>>(omega_sub, qd, shifts, n_mont, xs, l1inv);
   CAPGPU_LAUNCH_CHECK(ctx);
 }
 

@@ -57,10 +57,19 @@ void fill_pi(capgpu_ctx* ctx, Fr* dst, size_t stride, size_t n, int G, const Fr*
 // wires: [5][G] rows of wstride; num / den / z: G rows of n; cn / cd: G rows of cstride
 void grand_product(capgpu_ctx* ctx, const Fr* wires, size_t wstride, const Fr* sig_eval, const Fr* omega_pows, size_t n, int G,
                    const GpArgs* args, Fr* num, Fr* den, Fr* cn, Fr* cd, size_t cstride, Fr* z);
+// The quotient domain is `cosets` cosets s_k H of `sub` points each (m = cosets * sub): one coset of 8n points (s_0 = g), or the
+// three cosets g rho^k H_2n of the 6n-point domain.  Point (k, i) = s_k w_sub^i sits at index k * sub + i; w_n x is `step` = sub / n
+// places further inside the coset; Z_H(x) = s_k^n (w_sub^n)^i - 1 has period `step` in i: zh_inv[k * step + (i mod step)].
+struct QuotDomain {
+  size_t m, sub;
+  uint32_t log_sub, step;
+};
 // coset: [7][G] rows of m; out: G rows of m
 void quotient_evals(capgpu_ctx* ctx, const Fr* coset, const Fr* sel, const Fr* sig, const Fr* xs, const Fr* l1inv, const Fr* zh_inv,
-                    size_t m, int G, const QuotArgs* args, Fr* out);
-void coset_tables(capgpu_ctx* ctx, const Fr* omega_m, size_t m, const Fr& gen, const Fr& n_mont, Fr* xs, Fr* l1inv);
+                    const QuotDomain& qd, int G, const QuotArgs* args, Fr* out);
+// xs[k * sub + i] = shift[k] * omega_sub[i], l1inv = 1 / (n (xs - 1))
+struct CosetShifts { Fr s[3]; };
+void coset_tables(capgpu_ctx* ctx, const Fr* omega_sub, const QuotDomain& qd, const CosetShifts& shifts, const Fr& n_mont, Fr* xs, Fr* l1inv);
 // t: G rows of m; split: [5][G] rows of stride; flag[g]
 void split_quotient(capgpu_ctx* ctx, const Fr* t, size_t n, size_t m, int G, Fr* split, size_t stride, const BlindArgs* args, uint32_t* flag);
 // out: G rows of 16 (10 used); scratch: G x 160

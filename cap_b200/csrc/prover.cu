@@ -37,6 +37,15 @@ static const uint64_t kHostRoot28[4] = {0x636e735580d13d9cull, 0xa22bf3742445ffd
 static const uint64_t kHostGen[4] = {0x1b0d0ef99fffffe6ull, 0xeaba68a3a32a913full, 0x47d8eb76d8dd0689ull, 0x15d0085520f5bbc3ull};
 
 static inline Fr to_dev(const HFr& x) { Fr r; memcpy(r.v, x.v, 32); return r; }
+// rho = 5^((r-1) / (3 * 2^28)) in Montgomery form (ntt.cu kRho28): host_rho(L) has order 3 * 2^L and host_rho(L)^3 = host_omega(L)
+static const uint64_t kHostRho28[4] = {0x70f4a36d938bb649ull, 0xb81a7492f4178187ull, 0x22e5d04469f2125eull, 0x0a0b84166fdced23ull};
+static inline HFr host_rho(unsigned log_n) {
+  HFr w = HFr::from_limbs(kHostRho28);
+  for (unsigned i = 0; i < 28 - log_n; i++) w = w.sqr();
+  return w;
+}
+static inline QuotDomain quot_domain(const capgpu_pk* pk) { return QuotDomain{pk->m, pk->qsub, pk->qlog_sub, pk->qstep}; }
+
 static inline HFr host_omega(unsigned log_n) {
   HFr w = HFr::from_limbs(kHostRoot28);
   for (unsigned i = 0; i < 28 - log_n; i++) w = w.sqr();
@@ -291,10 +300,13 @@ void round3(capgpu_job* job, const uint64_t* const* alpha, const uint64_t* const
   }
   upload_args(job, job->d_quot, job->h_quot);
   upload_args(job, job->d_blind, job->h_blind);
-  // coset evaluations of the 5 wire polys, PI and z on the 8n domain (selectors / sigmas are cached in the pk)
-  ntt_device(ctx, pk->log_n + 3, job->polys, n + 3, NP, job->coset, m, job->ntt_tmp, 7 * G, false, true);
-  quotient_evals(ctx, job->coset, pk->sel_coset, pk->sig_coset, pk->xs, pk->l1inv, pk->zh_inv, m, G, job->d_quot, job->t);
-  ntt_device(ctx, pk->log_n + 3, job->t, m, m, job->t, m, job->ntt_tmp, G, true, true);
+  // evaluations of the 5 wire polys, PI and z on the quotient domain (selectors / sigmas are cached in the pk): 6n points as three
+  // 2n-point cosets, or the 8n-point coset for tiny circuits
+  if (pk->q3) ntt3_forward(ctx, pk->log_n + 1, job->polys, n + 3, NP, job->coset, job->ntt_tmp, 7 * G);
+  else ntt_device(ctx, pk->log_n + 3, job->polys, n + 3, NP, job->coset, m, job->ntt_tmp, 7 * G, false, true);
+  quotient_evals(ctx, job->coset, pk->sel_coset, pk->sig_coset, pk->xs, pk->l1inv, pk->zh_inv, quot_domain(pk), G, job->d_quot, job->t);
+  if (pk->q3) ntt3_inverse(ctx, pk->log_n + 1, job->t, job->ntt_tmp, G, pk->q_z1, pk->q_gi1, pk->q_gi2);
+  else ntt_device(ctx, pk->log_n + 3, job->t, m, m, job->t, m, job->ntt_tmp, G, true, true);
   split_quotient(ctx, job->t, n, m, G, job->split, NP, job->d_blind, job->flag);
   msm_device(ctx, pk->srs, 0, job->split, n + 3, NP, 5 * G, true, job->comms_dev, ctx->latency_mode);
   CAPGPU_CUDA(cudaMemcpyAsync(job->h_flag, job->flag, G * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
@@ -397,29 +409,51 @@ void pk_finish(capgpu_ctx* ctx, capgpu_pk* pk) {
   CAPGPU_CUDA(cudaMalloc(&pk->xs, m * sizeof(Fr)));
   CAPGPU_CUDA(cudaMalloc(&pk->l1inv, m * sizeof(Fr)));
   CAPGPU_CUDA(cudaMalloc(&pk->zh_inv, 8 * sizeof(Fr)));
+  const unsigned log_sub = pk->qlog_sub;
   CAPGPU_CUDA(cudaMalloc(&pk->omega_n, n * sizeof(Fr)));
   ctx->ntt_tmp.reserve(5 * m * sizeof(Fr));
   Fr* tmp = ctx->ntt_tmp.as<Fr>();
   ntt_device(ctx, pk->log_n, pk->sig_coef, n, n, pk->sig_eval, n, tmp, 5, false, false);
-  for (int s = 0; s < 13; s++)
-    ntt_device(ctx, pk->log_n + 3, pk->sel_coef + (size_t)s * n, n, n, pk->sel_coset + (size_t)s * m, m, tmp, 1, false, true);
-  ntt_device(ctx, pk->log_n + 3, pk->sig_coef, n, n, pk->sig_coset, m, tmp, 5, false, true);
+  for (int s = 0; s < 13; s++) {
+    if (pk->q3) ntt3_forward(ctx, log_sub, pk->sel_coef + (size_t)s * n, n, n, pk->sel_coset + (size_t)s * m, tmp, 1);
+    else ntt_device(ctx, log_sub, pk->sel_coef + (size_t)s * n, n, n, pk->sel_coset + (size_t)s * m, m, tmp, 1, false, true);
+  }
+  if (pk->q3) ntt3_forward(ctx, log_sub, pk->sig_coef, n, n, pk->sig_coset, tmp, 5);
+  else ntt_device(ctx, log_sub, pk->sig_coef, n, n, pk->sig_coset, m, tmp, 5, false, true);
   CAPGPU_CUDA(cudaMemcpyAsync(pk->omega_n, domain_omega_powers(ctx, pk->log_n), n * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
   {
     const char* e = getenv("CAPGPU_LAGRANGE");
     if (!(e && atoi(e) == 0) && pk->srs->n >= n + 2)
       pk->lag = srs_lagrange(ctx, pk->srs, pk->log_n, pk->omega_n, to_dev(HFr::from_u64(n).inv()));
   }
-  HFr gen = HFr::from_limbs(kHostGen);
-  coset_tables(ctx, domain_omega_powers(ctx, pk->log_n + 3), m, to_dev(gen), to_dev(HFr::from_u64(n)), pk->xs, pk->l1inv);
-  HFr wm = host_omega(pk->log_n + 3);
+  // coset shifts s_k = g rho^k (one coset, s_0 = g, on the 8n domain); 1 / Z_H has period `qstep` along a coset
+  const HFr gen = HFr::from_limbs(kHostGen);
+  const HFr rho = pk->q3 ? host_rho(log_sub) : HFr::one();
+  const int cosets = pk->q3 ? 3 : 1;
+  CosetShifts shifts;
+  HFr sk = gen;
+  const HFr wsub = host_omega(log_sub);
   Fr zh[8];
-  HFr x = gen;
-  for (int i = 0; i < 8; i++) {
-    zh[i] = to_dev((x.pow_u64(n) - HFr::one()).inv());
-    x = x * wm;
+  for (int k = 0; k < 3; k++) {
+    shifts.s[k] = to_dev(sk);
+    if (k < cosets) {
+      HFr x = sk;
+      for (unsigned i = 0; i < pk->qstep; i++) {
+        zh[k * pk->qstep + i] = to_dev((x.pow_u64(n) - HFr::one()).inv());
+        x = x * wsub;
+      }
+    }
+    sk = sk * rho;
   }
-  CAPGPU_CUDA(cudaMemcpyAsync(pk->zh_inv, zh, sizeof zh, cudaMemcpyHostToDevice, ctx->stream));
+  coset_tables(ctx, domain_omega_powers(ctx, log_sub), quot_domain(pk), shifts, to_dev(HFr::from_u64(n)), pk->xs, pk->l1inv);
+  CAPGPU_CUDA(cudaMemcpyAsync(pk->zh_inv, zh, cosets * pk->qstep * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
+  if (pk->q3) {
+    // ntt3_inverse: zeta = rho^(2n) is a primitive cube root of unity; c_k = s_k^(2n) = g^(2n) zeta^k
+    const HFr gi1 = gen.pow_u64(pk->qsub).inv();
+    pk->q_z1 = to_dev(rho.pow_u64(pk->qsub).inv());
+    pk->q_gi1 = to_dev(gi1);
+    pk->q_gi2 = to_dev(gi1.sqr());
+  }
   ctx_wait(ctx);
   // transcript bytes of the verifying key (SolidityTranscript::append_vk_and_pub_input, minus the inputs)
   SolidityTranscript t;
@@ -438,7 +472,14 @@ capgpu_pk* pk_alloc(capgpu_ctx* ctx, const capgpu_srs* srs, unsigned log_n, size
   pk->device = ctx->device;
   pk->log_n = log_n;
   pk->n = (size_t)1 << log_n;
-  pk->m = pk->n * 8;
+  // Quotient domain: t has degree 5n + 7, so 6n points (three cosets of 2n, ntt.cu) carry it when n >= 8; tiny circuits and
+  // CAPGPU_QDOMAIN=8 keep the 8n-point coset of the next power of two (ark-poly's choice — same polynomial either way).
+  static const bool force8 = [] { const char* e = getenv("CAPGPU_QDOMAIN"); return e && atoi(e) == 8; }();
+  pk->q3 = !force8 && log_n >= 6;
+  pk->qlog_sub = pk->q3 ? log_n + 1 : log_n + 3;
+  pk->qsub = (size_t)1 << pk->qlog_sub;
+  pk->qstep = (unsigned)(pk->qsub / pk->n);
+  pk->m = pk->q3 ? 3 * pk->qsub : pk->qsub;
   pk->num_inputs = num_inputs;
   pk->srs = srs;
   for (int i = 0; i < 5; i++) pk->k[i] = HFr::from_limbs(k + 4 * i);
