@@ -318,7 +318,16 @@ __global__ void __launch_bounds__(128, MINB) msm_accumulate(const G1Affine* __re
     const uint32_t* ent = entries + b * entries_stride;
     heavy = end - start >= heavy_thr;  // left to msm_accumulate_heavy
     if (heavy) end = start;
-    for (uint32_t e = start + lane; e < end; e += LPB) {
+    uint32_t e = start + lane;
+    // the lane's first two entries are both affine: 6 products instead of a copy and a 10-product mixed addition
+    if (e < end && end - e > LPB) {
+      const uint32_t u0 = ent[e], u1 = ent[e + LPB];
+      const G1Affine p0 = table[u0 & 0x7fffffffu], p1 = table[u1 & 0x7fffffffu];
+      if (!p0.is_inf() && !p1.is_inf()) {  // (otherwise the loop below takes them one at a time)
+        if (xyzz_set_affine2(acc, p0.x, (u0 >> 31) ? fp_neg(p0.y) : p0.y, p1.x, (u1 >> 31) ? fp_neg(p1.y) : p1.y)) e += 2 * LPB;
+      }
+    }
+    for (; e < end; e += LPB) {
       uint32_t u = ent[e];
       G1Affine p = table[u & 0x7fffffffu];
       if (!p.is_inf()) xyzz_add_mixed(acc, p.x, p.y, (u >> 31) != 0);
