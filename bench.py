@@ -491,15 +491,19 @@ def side_measurements(args, torch, ctxs, pk, srs, circ, wires_dev, wires, pubs, 
     a = torch.randint(0, 1 << 60, (gb, m, 4), dtype=torch.int64, device="cuda", generator=g)
     b = torch.empty_like(a)
     grp_ms = time_on_stream(lambda: _lib.check(lib.capgpu_ntt_dev(ctx.h, c_void_p(a.data_ptr()), m, c_void_p(b.data_ptr()), log_m, gb, 0, 1), ctx.h), reps=5)
-    # ... and with the input length the prover really has (n + 3 coefficients, zero-extended to 8n: the first three
-    # stages of the column pass then only copy and scale)
+    # ... and what the prover really issues since the quotient moved to the 6n-point domain: three 2n-point coset transforms
+    # per polynomial from its n + 3 coefficients (capgpu_ntt3_dev), plus the inverse with its radix-3 step for the quotient
     a3 = a.view(-1, 4)[: gb * (circ.n + 3)].view(gb, circ.n + 3, 4)
-    short_ms = time_on_stream(lambda: _lib.check(lib.capgpu_ntt_dev(ctx.h, c_void_p(a3.data_ptr()), circ.n + 3, c_void_p(b.data_ptr()), log_m, gb, 0, 1), ctx.h), reps=5)
+    b3 = b.view(-1, 4)[: gb * 6 * circ.n]
+    short_ms = time_on_stream(lambda: _lib.check(lib.capgpu_ntt3_dev(ctx.h, c_void_p(a3.data_ptr()), circ.n + 3, c_void_p(b3.data_ptr()), circ.log_n + 1, gb, 0), ctx.h), reps=5)
+    inv_ms = time_on_stream(lambda: _lib.check(lib.capgpu_ntt3_dev(ctx.h, c_void_p(b3.data_ptr()), 6 * circ.n, c_void_p(b3.data_ptr()), circ.log_n + 1, args.group, 1), ctx.h), reps=5)
     out["ntt"]["lockstep_group"] = {"size": f"{gb} x 2^{log_m} coset NTT (7 per proof x group of {args.group})", "ms": grp_ms, "ms_per_7": grp_ms / args.group,
+                                    "quotient_domain": f"6n = 3 cosets x 2^{circ.log_n + 1}",
                                     "ms_per_7_from_n_plus_3_coefficients": short_ms / args.group,
+                                    "ms_per_quotient_inverse": inv_ms / args.group,
                                     "gbutterflies_per_s": gb * (m / 2) * log_m / (grp_ms * 1e-3) * 1e-9,
                                     "frac_of_fmul_microbench": gb * (m / 2) * log_m / (grp_ms * 1e-3) * 1e-9 / calib["gfmul_per_s"],
-                                    "note": "ncu (profiles/r2_ncu_ntt_group8_raw.csv): sm__pipe_fmaheavy_cycles_active 90 % / 88 % of elapsed in the two passes"}
+                                    "note": "ncu (profiles/r2_ncu_ntt_group8_raw.csv, 8n build): sm__pipe_fmaheavy_cycles_active 90 % / 88 % of elapsed in the two passes"}
     del a, b
     n17 = 1 << 17
     srs17 = device.Srs(ctx, tau_mont=field.fr_to_mont_array([TAU % field.R])[0], size=n17)

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, "libcapgpu.so")
 # every symbol include/capgpu.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "capgpu_strerror", "capgpu_last_error", "capgpu_ctx_create", "capgpu_ctx_destroy", "capgpu_ctx_sync",
-    "capgpu_ctx_stream", "capgpu_srs_upload", "capgpu_srs_setup", "capgpu_srs_export", "capgpu_msm_g1_dev", "capgpu_ntt_dev", "capgpu_srs_destroy", "capgpu_srs_size", "capgpu_msm_g1",
+    "capgpu_ctx_stream", "capgpu_srs_upload", "capgpu_srs_setup", "capgpu_srs_export", "capgpu_msm_g1_dev", "capgpu_ntt_dev", "capgpu_ntt3_dev", "capgpu_srs_destroy", "capgpu_srs_size", "capgpu_msm_g1",
     "capgpu_ntt", "capgpu_pk_upload", "capgpu_preprocess", "capgpu_pk_export", "capgpu_pk_destroy", "capgpu_pk_lagrange", "capgpu_pk_lagrange_export", "capgpu_msm_g1_adhoc",
     "capgpu_prove", "capgpu_job_begin", "capgpu_job_round1", "capgpu_job_round2", "capgpu_job_round3",
     "capgpu_job_round4", "capgpu_job_round5", "capgpu_job_end", "capgpu_debug_read", "capgpu_launch_count",
@@ -88,6 +88,7 @@ def load() -> ctypes.CDLL:
         "capgpu_srs_size": (c_size_t, [c_void_p]),
         "capgpu_msm_g1": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_size_t, c_size_t, c_int, c_void_p]),
         "capgpu_ntt": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_uint, c_size_t, c_int, c_int]),
+        "capgpu_ntt3_dev": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_uint, c_size_t, c_int]),
         "capgpu_pk_upload": (c_int, [c_void_p, c_void_p, c_uint, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, POINTER(c_void_p)]),
         "capgpu_preprocess": (c_int, [c_void_p, c_void_p, c_uint, c_size_t, c_void_p, c_void_p, c_void_p, POINTER(c_void_p)]),
         "capgpu_pk_export": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

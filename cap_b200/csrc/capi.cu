@@ -113,6 +113,24 @@ extern "C" int capgpu_ntt_dev(capgpu_ctx* ctx, const void* d_in, size_t in_len, 
   });
 }
 
+extern "C" int capgpu_ntt3_dev(capgpu_ctx* ctx, const void* d_in, size_t in_len, void* d_out, unsigned log_n, size_t batch, int inverse) {
+  if (!ctx || !d_in || !d_out) return CAPGPU_ERR_ARG;
+  return guarded(ctx, [&] {
+    CAPGPU_REQUIRE(log_n >= 1 && log_n <= 20, "NTT size must be 2^1 .. 2^20");
+    const size_t n = (size_t)1 << log_n;
+    ctx->ntt_tmp.reserve(3 * batch * n * sizeof(Fr));
+    if (inverse) {
+      CAPGPU_REQUIRE(in_len == 3 * n, "the inverse takes all 3 * 2^log_n values");
+      if (d_in != d_out) CAPGPU_CUDA(cudaMemcpyAsync(d_out, d_in, batch * 3 * n * sizeof(Fr), cudaMemcpyDeviceToDevice, ctx->stream));
+      ntt3_inverse(ctx, log_n, (Fr*)d_out, ctx->ntt_tmp.as<Fr>(), batch);
+    } else {
+      CAPGPU_REQUIRE(in_len >= 1 && in_len <= n, "NTT input length out of range");
+      CAPGPU_REQUIRE(d_in != d_out, "the forward 3-coset transform is out of place");
+      ntt3_forward(ctx, log_n, (const Fr*)d_in, in_len, in_len, (Fr*)d_out, ctx->ntt_tmp.as<Fr>(), batch);
+    }
+  });
+}
+
 // ------------------------------------------------------------------------------------------
 // calibration: integer multiply-add issue rate (the roofline denominator for MSM / NTT)
 // ------------------------------------------------------------------------------------------

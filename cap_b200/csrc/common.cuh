@@ -163,9 +163,9 @@ void ntt_device(capgpu_ctx* ctx, unsigned log_n, const Fr* src, size_t src_len, 
                 size_t dst_stride, Fr* tmp, size_t batch, bool inverse, bool coset);
 const Fr* domain_omega_powers(capgpu_ctx* ctx, unsigned log_n);  // omega^j, j < n (device)
 // The 3 * 2^log_n-point domain g <rho> as three cosets (ntt.cu): forward writes rows (b, k) of N = 2^log_n values, dst stride 3N per
-// input; inverse turns such rows into the 3N coefficients in place (z1 = zeta^-1, gi1 = g^-N, gi2 = g^-2N, host-computed).
+// input; inverse turns such rows into the 3N coefficients in place.
 void ntt3_forward(capgpu_ctx* ctx, unsigned log_n, const Fr* src, size_t src_len, size_t src_stride, Fr* dst, Fr* tmp, size_t batch);
-void ntt3_inverse(capgpu_ctx* ctx, unsigned log_n, Fr* t, Fr* tmp, size_t batch, const Fr& z1, const Fr& gi1, const Fr& gi2);
+void ntt3_inverse(capgpu_ctx* ctx, unsigned log_n, Fr* t, Fr* tmp, size_t batch);
 
 // ---- msm.cu -----------------------------------------------------------------------------
 // scalars: device, batch vectors of n Fr (stride `stride`); out: device, batch affine points.

@@ -38,6 +38,7 @@ struct NttVariant {
   Fr* pre = nullptr;
   Fr* mid = nullptr;
   Fr* post = nullptr;
+  Fr* rc = nullptr;  // 3-coset inverse only: zeta^-1, g^-N, g^-2N of the radix-3 step
   bool built = false;
 };
 
@@ -153,6 +154,14 @@ NttDomain* get_domain(capgpu_ctx* ctx, unsigned log_n) {
   return d;
 }
 
+// constants of ntt3_recombine_kernel: zeta = rho^N is the same primitive cube root of unity for every N = 2^log_n
+__global__ void ntt3_consts_kernel(Fr* out, unsigned log_n) {
+  const Fr gi1 = sqr_times(load_const(kGenInv), log_n);
+  out[0] = sqr_times(load_const(kRho28Inv), 28);
+  out[1] = gi1;
+  out[2] = fp_sqr(gi1);
+}
+
 static void build_variant(capgpu_ctx* ctx, NttDomain* d, bool inverse, int coset) {
   NttVariant& v = coset == 2 ? d->var3[inverse] : d->var[inverse][coset];
   if (v.built) return;
@@ -161,6 +170,11 @@ static void build_variant(capgpu_ctx* ctx, NttDomain* d, bool inverse, int coset
   if (two_pass) v.mid = build_table(ctx, d->n, TBL_MID, d->log_n, d->log_c, inverse, inverse && coset == 2 ? 1 : coset);
   if (coset && !inverse) v.pre = build_table(ctx, (size_t)1 << d->log_r, TBL_PRE, d->log_n, d->log_c, 0, coset);
   if (inverse && (coset || !two_pass)) v.post = build_table(ctx, d->n, TBL_POST, d->log_n, d->log_c, 1, coset);
+  if (inverse && coset == 2) {
+    CAPGPU_CUDA(cudaMalloc(&v.rc, 3 * sizeof(Fr)));
+    ntt3_consts_kernel<<<1, 1, 0, ctx->stream>>>(v.rc, d->log_n);
+    CAPGPU_LAUNCH_CHECK(ctx);
+  }
   v.built = true;
 }
 
@@ -179,6 +193,7 @@ void destroy_domain(NttDomain* d) {
       if (v.pre) cudaFree(v.pre);
       if (v.mid) cudaFree(v.mid);
       if (v.post) cudaFree(v.post);
+      if (v.rc) cudaFree(v.rc);
     }
   }
   if (d->omega_pows) cudaFree(d->omega_pows);
@@ -555,11 +570,12 @@ void ntt3_forward(capgpu_ctx* ctx, unsigned log_n, const Fr* src, size_t src_len
   ntt_run(ctx, log_n, src, src_len, src_stride, dst, (size_t)1 << log_n, tmp, batch, false, 2);
 }
 
-// u_k in rows (b, k) of `t` -> coefficients t_0 .. t_{3N-1} in place; z1 = zeta^-1, gi1 = g^-N, gi2 = g^-2N (the 1/3 is in the
-// inverse transforms' post table).  With zeta^-2 = -1 - zeta^-1 the step costs two products plus the two scalings per j.
-__global__ void ntt3_recombine_kernel(Fr* t, uint32_t N, Fr z1, Fr gi1, Fr gi2) {
+// u_k in rows (b, k) of `t` -> coefficients t_0 .. t_{3N-1} in place; rc = {zeta^-1, g^-N, g^-2N} (the 1/3 is in the inverse
+// transforms' post table).  With zeta^-2 = -1 - zeta^-1 the step costs two products plus the two scalings per j.
+__global__ void ntt3_recombine_kernel(Fr* t, uint32_t N, const Fr* __restrict__ rc) {
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= N) return;
+  const Fr z1 = rc[0], gi1 = rc[1], gi2 = rc[2];
   Fr* row = t + (size_t)blockIdx.y * 3 * N;
   const Fr u0 = row[j], u1 = row[N + j], u2 = row[2 * (size_t)N + j];
   const Fr p1 = fp_mul(z1, u1), q1 = fp_mul(z1, u2);
@@ -571,12 +587,12 @@ __global__ void ntt3_recombine_kernel(Fr* t, uint32_t N, Fr z1, Fr gi1, Fr gi2) 
   row[2 * (size_t)N + j] = fp_mul(a2, gi2);
 }
 
-void ntt3_inverse(capgpu_ctx* ctx, unsigned log_n, Fr* t, Fr* tmp, size_t batch, const Fr& z1, const Fr& gi1, const Fr& gi2) {
+void ntt3_inverse(capgpu_ctx* ctx, unsigned log_n, Fr* t, Fr* tmp, size_t batch) {
   const size_t N = (size_t)1 << log_n;
   ntt_run(ctx, log_n, t, N, N, t, N, tmp, batch, true, 2);
   if (batch == 0) return;
   ProfScope prof(ctx, PROF_NTT, (double)batch * 2.0 * (double)N);
-  ntt3_recombine_kernel<<<dim3((unsigned)ceil_div(N, 128), (unsigned)batch), 128, 0, ctx->stream>>>(t, (uint32_t)N, z1, gi1, gi2);
+  ntt3_recombine_kernel<<<dim3((unsigned)ceil_div(N, 128), (unsigned)batch), 128, 0, ctx->stream>>>(t, (uint32_t)N, get_domain(ctx, log_n)->var3[1].rc);
   CAPGPU_LAUNCH_CHECK(ctx);
 }
 

@@ -305,7 +305,7 @@ void round3(capgpu_job* job, const uint64_t* const* alpha, const uint64_t* const
   if (pk->q3) ntt3_forward(ctx, pk->log_n + 1, job->polys, n + 3, NP, job->coset, job->ntt_tmp, 7 * G);
   else ntt_device(ctx, pk->log_n + 3, job->polys, n + 3, NP, job->coset, m, job->ntt_tmp, 7 * G, false, true);
   quotient_evals(ctx, job->coset, pk->sel_coset, pk->sig_coset, pk->xs, pk->l1inv, pk->zh_inv, quot_domain(pk), G, job->d_quot, job->t);
-  if (pk->q3) ntt3_inverse(ctx, pk->log_n + 1, job->t, job->ntt_tmp, G, pk->q_z1, pk->q_gi1, pk->q_gi2);
+  if (pk->q3) ntt3_inverse(ctx, pk->log_n + 1, job->t, job->ntt_tmp, G);
   else ntt_device(ctx, pk->log_n + 3, job->t, m, m, job->t, m, job->ntt_tmp, G, true, true);
   split_quotient(ctx, job->t, n, m, G, job->split, NP, job->d_blind, job->flag);
   msm_device(ctx, pk->srs, 0, job->split, n + 3, NP, 5 * G, true, job->comms_dev, ctx->latency_mode);
@@ -447,13 +447,6 @@ void pk_finish(capgpu_ctx* ctx, capgpu_pk* pk) {
   }
   coset_tables(ctx, domain_omega_powers(ctx, log_sub), quot_domain(pk), shifts, to_dev(HFr::from_u64(n)), pk->xs, pk->l1inv);
   CAPGPU_CUDA(cudaMemcpyAsync(pk->zh_inv, zh, cosets * pk->qstep * sizeof(Fr), cudaMemcpyHostToDevice, ctx->stream));
-  if (pk->q3) {
-    // ntt3_inverse: zeta = rho^(2n) is a primitive cube root of unity; c_k = s_k^(2n) = g^(2n) zeta^k
-    const HFr gi1 = gen.pow_u64(pk->qsub).inv();
-    pk->q_z1 = to_dev(rho.pow_u64(pk->qsub).inv());
-    pk->q_gi1 = to_dev(gi1);
-    pk->q_gi2 = to_dev(gi1.sqr());
-  }
   ctx_wait(ctx);
   // transcript bytes of the verifying key (SolidityTranscript::append_vk_and_pub_input, minus the inputs)
   SolidityTranscript t;

@@ -18,7 +18,6 @@ struct capgpu_pk {
   bool q3 = false;
   size_t qsub = 0;
   unsigned qlog_sub = 0, qstep = 0;
-  capgpu::Fr q_z1, q_gi1, q_gi2;  // radix-3 recombination constants of ntt3_inverse (q3 only)
   const capgpu_srs* srs = nullptr;
   capgpu_srs* owned_srs = nullptr;  // commit key embedded in a serialized ProvingKey (freed with the key)
   capgpu_srs* lag = nullptr;        // Lagrange-basis commit key [L_0..L_{n-1}, P_0, P_1, P_n, P_{n+1}] (owned)

@@ -83,6 +83,25 @@ class Context:
         _lib.check(self.lib.capgpu_ntt(self.h, _ptr(a), in_len, _ptr(out), log_n, batch, int(inverse), int(coset)), self.h)
         return out[0] if single else out
 
+    def ntt3(self, data, log_n: int, inverse: bool = False) -> np.ndarray:
+        """Transforms on the 3 * 2^log_n-point domain g <rho> the prover evaluates the quotient on (capgpu_ntt3_dev; the
+        buffers pass through torch device tensors).  Forward: (batch, in_len <= 2^log_n, 4) coefficients ->
+        (batch, 3, 2^log_n, 4) values, value (k, i) = f(g rho^k w^i).  Inverse: (batch, 3, 2^log_n, 4) values ->
+        (batch, 3 * 2^log_n, 4) coefficients."""
+        import torch
+
+        a = np.ascontiguousarray(data, dtype=np.uint64)
+        n = 1 << log_n
+        if inverse:
+            a = a.reshape(-1, 3 * n, 4)
+        batch, in_len, _ = a.shape
+        d_in = torch.from_numpy(a.view(np.int64)).cuda()
+        d_out = torch.empty((batch, 3 * n, 4), dtype=torch.int64, device="cuda")
+        _lib.check(self.lib.capgpu_ntt3_dev(self.h, c_void_p(d_in.data_ptr()), in_len, c_void_p(d_out.data_ptr()), log_n, batch, int(inverse)), self.h)
+        self.sync()
+        out = d_out.cpu().numpy().view(np.uint64)
+        return out if inverse else out.reshape(batch, 3, n, 4)
+
 
 class Srs:
     """Device-resident commit key (``powers_of_g``), with the MSM's window-shifted tables."""

@@ -159,6 +159,14 @@ int capgpu_ntt(capgpu_ctx* ctx, const uint64_t* in, size_t in_len, uint64_t* out
 int capgpu_ntt_dev(capgpu_ctx* ctx, const void* d_in, size_t in_len, void* d_out, unsigned log_n, size_t batch,
                    int inverse, int coset);
 
+/* The 3 * 2^log_n-point domain g <rho> (rho = 5^((r-1) / (3 * 2^log_n))), stored as its three cosets g rho^k H, k-major: value
+ * (k, i) = f(g rho^k w^i) sits at index k * 2^log_n + i.  The prover evaluates the quotient (degree 5n + 7) on 6n points this
+ * way (log_n = log2(2n)) where jf-plonk's compute_quotient_polynomial uses ark-poly's 8n-point coset; both interpolate the same
+ * polynomial.  Forward (inverse == 0): d_in holds `batch` vectors of in_len <= 2^log_n coefficients, d_out receives
+ * batch x 3 * 2^log_n values (out of place).  Inverse: in_len == 3 * 2^log_n values per vector -> the 3 * 2^log_n coefficients
+ * (d_in == d_out allowed).  Device pointers; asynchronous on the ctx stream. */
+int capgpu_ntt3_dev(capgpu_ctx* ctx, const void* d_in, size_t in_len, void* d_out, unsigned log_n, size_t batch, int inverse);
+
 /* ---- proving key --------------------------------------------------------------------------
  * Mirrors jf-plonk 0.1.2 `ProvingKey { sigmas, selectors, commit_key, vk }` as embedded at
  * /root/reference/src/proof/transfer.rs:60 (built by `preprocess`, :124-155).

@@ -62,6 +62,7 @@ extern "C" {
     pub fn capgpu_msm_g1_adhoc(ctx: *mut capgpu_ctx, points_xy: *const u64, scalars: *const u64, n: usize, scalars_mont: c_int, out_xy: *mut u64) -> c_int;
     pub fn capgpu_g1_sum_dev(ctx: *mut capgpu_ctx, d_points_xy: *const c_void, count: usize, d_out_xy: *mut c_void) -> c_int;
     pub fn capgpu_ntt_dev(ctx: *mut capgpu_ctx, d_in: *const c_void, in_len: usize, d_out: *mut c_void, log_n: c_uint, batch: usize, inverse: c_int, coset: c_int) -> c_int;
+    pub fn capgpu_ntt3_dev(ctx: *mut capgpu_ctx, d_in: *const c_void, in_len: usize, d_out: *mut c_void, log_n: c_uint, batch: usize, inverse: c_int) -> c_int;
     pub fn capgpu_preprocess(ctx: *mut capgpu_ctx, srs: *const capgpu_srs, log_n: c_uint, num_inputs: usize, selector_evals: *const u64, sigma_evals: *const u64, k: *const u64, out: *mut *mut capgpu_pk) -> c_int;
     pub fn capgpu_pk_export(ctx: *mut capgpu_ctx, pk: *const capgpu_pk, selectors: *mut u64, sigmas: *mut u64, selector_comms_xy: *mut u64, sigma_comms_xy: *mut u64) -> c_int;
     pub fn capgpu_pk_lagrange(pk: *mut capgpu_pk, enable: c_int) -> c_int;

@@ -84,12 +84,75 @@ def test_ntt_round_trip_and_linearity_at_bench_sizes(ctx, log_n):
         assert got == ontt.poly_eval(coeffs, 5 * pow(w, i, B.R) % B.R)
 
 
+def _rho(log_n):
+    """Generator of the 3 * 2^log_n-point quotient domain: 5^((r-1) / (3 * 2^log_n)), rho^3 = the 2^log_n-th root of unity."""
+    rho = pow(5, (B.R - 1) // (3 << log_n), B.R)
+    assert pow(rho, 3, B.R) == B.fr_root_of_unity(log_n)
+    return rho
+
+
+@pytest.mark.parametrize("log_n", [3, 7, 10, 11, 13])
+def test_ntt3_matches_oracle(ctx, log_n):
+    """capgpu_ntt3_dev against the oracle's coset transforms with the shifts 5 rho^k (one- and two-pass sizes), and its inverse
+    against the coefficients of a random polynomial of degree < 3N evaluated through the oracle."""
+    rng = random.Random(100 + log_n)
+    n = 1 << log_n
+    rho = _rho(log_n)
+    shifts = [5 * pow(rho, k, B.R) % B.R for k in range(3)]
+    for in_len in sorted({n, n // 2 + 3, 1}):
+        x = [rng.randrange(B.R) for _ in range(in_len)]
+        got = ctx.ntt3(field.fr_to_mont_array(x)[None], log_n)[0]
+        for k in range(3):
+            assert field.fr_from_mont_array(got[k]) == ontt.coset_fft(x, log_n, shifts[k]), (log_n, in_len, k)
+    # f = T_0 + X^N T_1 + X^2N T_2 on the coset s_k H: sum_a (s_k^N)^a T_a(s_k w^i)
+    coeffs = [rng.randrange(B.R) for _ in range(3 * n)]
+    vals = []
+    for k in range(3):
+        c = pow(shifts[k], n, B.R)
+        parts = [ontt.coset_fft(coeffs[a * n:(a + 1) * n], log_n, shifts[k]) for a in range(3)]
+        vals.append([(parts[0][i] + c * parts[1][i] + c * c % B.R * parts[2][i]) % B.R for i in range(n)])
+    vm = np.stack([field.fr_to_mont_array(v) for v in vals])[None]
+    assert field.fr_from_mont_array(ctx.ntt3(vm, log_n, inverse=True)[0]) == coeffs
+    # batch of two, rows independent
+    two = np.concatenate([vm, vm[:, ::-1]])
+    back = ctx.ntt3(two, log_n, inverse=True)
+    assert field.fr_from_mont_array(back[0]) == coeffs and not np.array_equal(back[0], back[1])
+
+
+def test_ntt3_at_the_prover_size(ctx):
+    """Size-independent checks at 2n = 2^16 (the transfer circuit's quotient domain): direct evaluation of a few points, and
+    inverse(forward) on a polynomial of the quotient's degree 5n + 7 assembled from three forward transforms."""
+    log_n = 16
+    n = 1 << log_n
+    g = np.random.default_rng(16)
+    a = g.integers(0, 1 << 62, size=(3, n, 4), dtype=np.uint64)
+    a[:, :, 3] &= (1 << 60) - 1
+    a[2, n // 2 + 8:] = 0  # degree 5 * (n / 2) + 7
+    rho, w = _rho(log_n), B.fr_root_of_unity(log_n)
+    f = ctx.ntt3(a, log_n)  # (3 chunks, 3 cosets, n, 4)
+    short = a[0, :48].copy()
+    fs = ctx.ntt3(short[None], log_n)[0]
+    cs = field.fr_from_mont_array(short)
+    for k, i in [(0, 0), (1, 1), (2, n // 2 + 3), (2, n - 1)]:
+        x = 5 * pow(rho, k, B.R) * pow(w, i, B.R) % B.R
+        assert field.fr_from_mont_array(fs[k, i:i + 1])[0] == ontt.poly_eval(cs, x)
+    vals = np.empty((3, n, 4), dtype=np.uint64)
+    for k in range(3):
+        c = pow(5 * pow(rho, k, B.R) % B.R, n, B.R)
+        t = [field.fr_from_mont_array(f[ch, k]) for ch in range(3)]
+        vals[k] = field.fr_to_mont_array([(t[0][i] + c * t[1][i] + c * c % B.R * t[2][i]) % B.R for i in range(n)])
+    back = ctx.ntt3(vals[None], log_n, inverse=True)[0]
+    assert np.array_equal(back, a.reshape(3 * n, 4))
+
+
 def test_ntt_argument_errors(ctx):
     a = np.zeros((4, 4), dtype=np.uint64)
     with pytest.raises(_lib.CapGpuError):
         ctx.ntt(a, 1)  # input longer than the domain
     with pytest.raises(_lib.CapGpuError):
         ctx.ntt(a, 21)  # unsupported size
+    with pytest.raises(_lib.CapGpuError):
+        ctx.ntt3(a[None], 1)  # input longer than 2^log_n
 
 
 @pytest.fixture(scope="module")
