@@ -356,7 +356,9 @@ __device__ __forceinline__ void ntt_phase_butterflies(Fr (&x)[8], uint32_t t, co
         Fr va = x[a], vb = x[b];
         x[a] = fp_add(va, vb);
         Fr d = fp_sub(va, vb);
-        if (log_m > 0) {
+        // twiddle w^0 = 1: the whole last stage, and in a tile's last phase (LOG_STRIDE == 0, lo == 0) every butterfly whose
+        // slot has k = 0 — known at compile time, 3 of the 8 products of a three-stage last phase
+        if (log_m > 0 && !(LOG_STRIDE == 0 && (i & (half - 1)) == 0)) {
           const uint32_t k = lo + ((uint32_t)(i & (half - 1)) << LOG_STRIDE);
           d = ntt_mul(d, tw[k << (9 - log_m)]);
         }

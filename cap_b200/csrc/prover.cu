@@ -111,7 +111,7 @@ capgpu_job* job_acquire(capgpu_ctx* ctx, const capgpu_pk* pk, int G, int cap_hin
   CAPGPU_REQUIRE(G >= 1 && G <= CAPGPU_MAX_GROUP, "group size out of range");
   capgpu_job* job = ctx->cached_job;
   if (job && job->busy) throw CodeError{CAPGPU_ERR_STATE};
-  if (job && (job->n != pk->n || job->num_inputs < pk->num_inputs || job->cap < G)) {
+  if (job && (job->n != pk->n || job->m != pk->m || job->num_inputs < pk->num_inputs || job->cap < G)) {
     capgpu_job_free_internal(job);
     ctx->cached_job = job = nullptr;
   }
@@ -467,7 +467,8 @@ capgpu_pk* pk_alloc(capgpu_ctx* ctx, const capgpu_srs* srs, unsigned log_n, size
   pk->n = (size_t)1 << log_n;
   // Quotient domain: t has degree 5n + 7, so 6n points (three cosets of 2n, ntt.cu) carry it when n >= 8; tiny circuits and
   // CAPGPU_QDOMAIN=8 keep the 8n-point coset of the next power of two (ark-poly's choice — same polynomial either way).
-  static const bool force8 = [] { const char* e = getenv("CAPGPU_QDOMAIN"); return e && atoi(e) == 8; }();
+  const char* qenv = getenv("CAPGPU_QDOMAIN");  // read per key, so one process can hold keys of both kinds (tests)
+  const bool force8 = qenv && atoi(qenv) == 8;
   pk->q3 = !force8 && log_n >= 6;
   pk->qlog_sub = pk->q3 ? log_n + 1 : log_n + 3;
   pk->qsub = (size_t)1 << pk->qlog_sub;

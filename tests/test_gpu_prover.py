@@ -385,6 +385,35 @@ def test_failed_round_releases_the_context(ctx):
     srs.close()
 
 
+@pytest.mark.parametrize("log_n,nin", [(6, 2), (9, 27), (11, 5)])
+def test_quotient_domains_agree(ctx, log_n, nin, monkeypatch):
+    """The 6n-point quotient domain (three 2n-point cosets; the default from n = 64) and the 8n-point coset jf-plonk uses
+    (CAPGPU_QDOMAIN=8) interpolate the same quotient: equal coefficients, equal proofs, and the same rejection of a bad witness."""
+    circ = synth.make_circuit(log_n, num_inputs=nin, seed=21)
+    n = circ.n
+    srs = plonk.PlonkKzgSnark.universal_setup(ctx, n + 2, TAU)
+    rng = random.Random(log_n)
+    bl = _mont([rng.randrange(B.R) for _ in range(17)])
+    bad = synth.SynthCircuit(circ.log_n, circ.num_inputs, circ.selectors, circ.wire_variables, list(circ.witness), circ.k)
+    v = bad.wire_variables[4][circ.num_inputs + 3]
+    bad.witness[v] = (bad.witness[v] + 1) % B.R
+    proofs, quotients, vk = [], [], None
+    for q in ("6", "8"):
+        monkeypatch.setenv("CAPGPU_QDOMAIN", q)
+        pk = plonk.PlonkKzgSnark.preprocess(ctx, srs, circ)
+        vk = pk.vk
+        proofs.append(plonk.PlonkKzgSnark.prove(ctx, circ, pk, bl, b"domains"))
+        t = plonk.debug_read(ctx, 4, 8 * n)
+        assert len(t) == (6 if q == "6" else 8) * n and not any(t[5 * n + 8:])
+        quotients.append(t[:5 * n + 8])
+        with pytest.raises(plonk.PlonkError, match="degree"):
+            plonk.PlonkKzgSnark.prove(ctx, bad, pk, bl, b"domains")
+        pk.close()
+    assert quotients[0] == quotients[1] and proofs[0] == proofs[1]
+    assert oplonk.verify(vk, plonk.public_input(circ), proofs[0], TAU, ext_msg=b"domains")
+    srs.close()
+
+
 @pytest.mark.parametrize("log_n", [3, 6, 9])
 def test_lagrange_commit_key(ctx, log_n):
     """The derived evaluation-form commit key is [L_j(tau) G] followed by P_0, P_1, P_n, P_{n+1}."""
