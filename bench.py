@@ -281,7 +281,7 @@ def run_capgpu(args):
             "host_threads_per_gpu": args.ctxs, "distinct_witnesses": N_WITNESSES,
             "witness": args.witness, "wire_commitments": "coefficient form" if args.no_lagrange else "evaluation form (Lagrange commit key)",
             "parallelism": f"{world} x independent-note shards, no collective",
-            "cache": "per-group working set (>1 GB workspace + 159 MB cached pk cosets) exceeds the 126 MB L2; no flush needed",
+            "cache": f"per-group working set (>1 GB workspace + {18 * 6 * circ.n * 32 / 1e6:.0f} MB cached pk evaluations on the 6n-point quotient domain) exceeds the 126 MB L2; no flush needed",
         },
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "proofs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
@@ -503,7 +503,7 @@ def side_measurements(args, torch, ctxs, pk, srs, circ, wires_dev, wires, pubs, 
                                     "ms_per_quotient_inverse": inv_ms / args.group,
                                     "gbutterflies_per_s": gb * (m / 2) * log_m / (grp_ms * 1e-3) * 1e-9,
                                     "frac_of_fmul_microbench": gb * (m / 2) * log_m / (grp_ms * 1e-3) * 1e-9 / calib["gfmul_per_s"],
-                                    "note": "ncu (profiles/r2_ncu_ntt_group8_raw.csv, 8n build): sm__pipe_fmaheavy_cycles_active 90 % / 88 % of elapsed in the two passes"}
+                                    "note": "ncu (profiles/r2_ncu_ntt3_quotient_group8_raw.csv): sm throughput 89 % / 86 % of peak in the two passes of the 168 x 2^16 quotient-domain transforms of a group of 8"}
     del a, b
     n17 = 1 << 17
     srs17 = device.Srs(ctx, tau_mont=field.fr_to_mont_array([TAU % field.R])[0], size=n17)

@@ -74,6 +74,47 @@ def coset_ifft(evals: list[int], log_n: int, shift: int = FR_GENERATOR) -> list[
     return c
 
 
+# ---- the 3 * 2^log_n-point domain of capgpu_ntt3_dev ------------------------------------------
+# Not a reference function: jf-plonk's compute_quotient_polynomial evaluates the quotient (degree 5n + 7) on ark-poly's
+# 8n-point coset; the CUDA prover uses the 6n points g <rho>, rho = 5^((r-1) / (6n)), as the three cosets g rho^k H_2n.
+# This is the checker for that transform; tests/test_oracle_ntt_msm.py shows both routes interpolate the same polynomial.
+def domain3_shifts(log_n: int) -> list[int]:
+    rho = pow(FR_GENERATOR, (R - 1) // (3 << log_n), R)
+    assert pow(rho, 3, R) == fr_root_of_unity(log_n)
+    return [FR_GENERATOR * pow(rho, k, R) % R for k in range(3)]
+
+
+def fft3(coeffs: list[int], log_n: int) -> list[list[int]]:
+    """values[k][i] = f(g rho^k w^i) for a polynomial of degree < 3 * 2^log_n."""
+    n = 1 << log_n
+    out = []
+    for s in domain3_shifts(log_n):
+        c = pow(s, n, R)
+        folded = [0] * n  # f mod (X^n - s^n) takes the same values on the coset s H
+        for j, v in enumerate(coeffs):
+            folded[j % n] = (folded[j % n] + v * pow(c, j // n, R)) % R
+        out.append(coset_fft(folded, log_n, s))
+    return out
+
+
+def ifft3(values: list[list[int]], log_n: int) -> list[int]:
+    """The 3 * 2^log_n coefficients from the values on the three cosets: per-coset interpolation u_k = f mod (X^n - c_k),
+    c_k = (g rho^k)^n = g^n zeta^k, then the 3 x 3 Vandermonde solve t_{j + an} = (1/3) g^(-an) sum_k zeta^(-ak) u_k[j]."""
+    n = 1 << log_n
+    shifts = domain3_shifts(log_n)
+    u = [coset_ifft(values[k], log_n, shifts[k]) for k in range(3)]
+    zeta_inv = inv(pow(shifts[1] * inv(shifts[0], R) % R, n, R), R)
+    gn_inv = inv(pow(shifts[0], n, R), R)
+    third = inv(3, R)
+    out = [0] * (3 * n)
+    for a in range(3):
+        scale = third * pow(gn_inv, a, R) % R
+        for j in range(n):
+            acc = sum(pow(zeta_inv, a * k, R) * u[k][j] for k in range(3)) % R
+            out[a * n + j] = acc * scale % R
+    return out
+
+
 def dft_naive(coeffs: list[int], log_n: int, shift: int = 1) -> list[int]:
     """O(n^2) definition, used to pin the fast transform on tiny sizes."""
     n = 1 << log_n

@@ -41,6 +41,23 @@ void emu_g1_add_mixed_chain(const uint32_t* pts, const int* negs, int n, uint32_
   }
   G1Affine r = xyzz_to_affine(acc); memcpy(out, &r, 64);
 }
+// the bucket walk of msm_accumulate (msm.cu): the first two entries through the affine + affine formula when both are finite
+// and their x differ, everything else through the mixed addition
+void emu_g1_bucket_chain(const uint32_t* pts, const int* negs, int n, uint32_t* out) {
+  G1XYZZ acc = G1XYZZ::inf();
+  int e = 0;
+  if (n >= 2) {
+    G1Affine p0, p1; memcpy(&p0, pts, 64); memcpy(&p1, pts + 16, 64);
+    if (!p0.is_inf() && !p1.is_inf()) {
+      if (xyzz_set_affine2(acc, p0.x, negs[0] ? fp_neg(p0.y) : p0.y, p1.x, negs[1] ? fp_neg(p1.y) : p1.y)) e = 2;
+    }
+  }
+  for (; e < n; e++) {
+    G1Affine p; memcpy(&p, pts + 16 * e, 64);
+    if (!p.is_inf()) xyzz_add_mixed(acc, p.x, p.y, negs[e] != 0);
+  }
+  G1Affine r = xyzz_to_affine(acc); memcpy(out, &r, 64);
+}
 void emu_g1_add_full(const uint32_t* pts_a, int na, const uint32_t* pts_b, int nb, uint32_t* out) {
   G1XYZZ a = G1XYZZ::inf(), b = G1XYZZ::inf();
   for (int i = 0; i < na; i++) { G1Affine p; memcpy(&p, pts_a + 16 * i, 64); if (!p.is_inf()) xyzz_add_mixed(a, p.x, p.y, false); }

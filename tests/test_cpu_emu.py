@@ -85,11 +85,12 @@ def test_batched_gcd_inversion(emu):
         assert _call(emu, f"emu_{pre}_inv", 0) == 0
 
 
-def _chain(emu, pts, negs):
-    a = g1_to_mont_array(pts)
-    ng = (ctypes.c_int * len(pts))(*negs)
+def _chain(emu, pts, negs, bucket=False):
+    a = g1_to_mont_array(pts) if pts else np.zeros((1, 8), dtype=np.uint64)
+    ng = (ctypes.c_int * max(len(pts), 1))(*negs)
     out = np.zeros(8, dtype=np.uint64)
-    emu.emu_g1_add_mixed_chain(a.ctypes.data_as(ctypes.c_void_p), ng, len(pts), out.ctypes.data_as(ctypes.c_void_p))
+    fn = emu.emu_g1_bucket_chain if bucket else emu.emu_g1_add_mixed_chain
+    fn(a.ctypes.data_as(ctypes.c_void_p), ng, len(pts), out.ctypes.data_as(ctypes.c_void_p))
     return g1_from_mont_array(out)[0]
 
 
@@ -116,6 +117,15 @@ def test_device_group_law(emu):
         ps = [rng.choice(pts) for _ in range(k)]
         negs = [rng.randrange(2) for _ in range(k)]
         assert _chain(emu, ps, negs) == ref(ps, negs)
+    # the accumulate kernel's bucket walk (affine + affine first addition) gives the same sums, exceptional starts included
+    for _ in range(20):
+        k = rng.randrange(0, 7)
+        ps = [rng.choice(pts + [None]) for _ in range(k)]
+        negs = [rng.randrange(2) for _ in range(k)]
+        assert _chain(emu, ps, negs, bucket=True) == ref(ps, negs)
+    Q = pts[1]
+    for ps, negs in [([Q, Q], [0, 0]), ([Q, Q], [1, 0]), ([Q, Q, Q], [0, 1, 1]), ([Q, Q, pts[2]], [1, 1, 0]), ([None, Q, Q], [0, 0, 0]), ([Q, None], [1, 0])]:
+        assert _chain(emu, ps, negs, bucket=True) == ref(ps, negs)
     P = pts[0]
     # exceptional cases of the mixed addition: doubling, cancellation, infinity operands
     assert _chain(emu, [P, P], [0, 0]) == B.g1_add(P, P)

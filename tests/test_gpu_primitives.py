@@ -104,6 +104,7 @@ def test_ntt3_matches_oracle(ctx, log_n):
         got = ctx.ntt3(field.fr_to_mont_array(x)[None], log_n)[0]
         for k in range(3):
             assert field.fr_from_mont_array(got[k]) == ontt.coset_fft(x, log_n, shifts[k]), (log_n, in_len, k)
+    assert shifts == ontt.domain3_shifts(log_n)
     # f = T_0 + X^N T_1 + X^2N T_2 on the coset s_k H: sum_a (s_k^N)^a T_a(s_k w^i)
     coeffs = [rng.randrange(B.R) for _ in range(3 * n)]
     vals = []
@@ -113,6 +114,8 @@ def test_ntt3_matches_oracle(ctx, log_n):
         vals.append([(parts[0][i] + c * parts[1][i] + c * c % B.R * parts[2][i]) % B.R for i in range(n)])
     vm = np.stack([field.fr_to_mont_array(v) for v in vals])[None]
     assert field.fr_from_mont_array(ctx.ntt3(vm, log_n, inverse=True)[0]) == coeffs
+    if log_n <= 10:  # the oracle's own restatement of the transform pair (O(n) modular powers per coefficient: small sizes)
+        assert vals == ontt.fft3(coeffs, log_n) and ontt.ifft3(vals, log_n) == coeffs
     # batch of two, rows independent
     two = np.concatenate([vm, vm[:, ::-1]])
     back = ctx.ntt3(two, log_n, inverse=True)

@@ -39,6 +39,33 @@ def test_ntt_golden(golden):
         assert ntt.coset_ifft(x, v["log_n"]) == _h(v["coset_ifft"])
 
 
+def test_quotient_domain_equivalence():
+    """N(x) / Z_H(x) evaluated point-wise on the 6n-point domain (three cosets of 2n points, oracle fft3 / ifft3 = the checker of
+    capgpu_ntt3_dev) interpolates the same quotient as on jf-plonk's 8n-point coset, for a quotient of the PLONK degree 5n + 7."""
+    rng = random.Random(6)
+    log_n = 4
+    n = 1 << log_n
+    t = [rng.randrange(B.R) for _ in range(5 * n + 8)]
+    numer = [0] * (len(t) + n)  # t * (X^n - 1)
+    for j, v in enumerate(t):
+        numer[j + n] = (numer[j + n] + v) % B.R
+        numer[j] = (numer[j] - v) % B.R
+    zh = [B.R - 1] + [0] * (n - 1) + [1]
+    # 8n-point coset (degree of the numerator 6n + 7 < 8n)
+    ev_n, ev_z = ntt.coset_fft(numer, log_n + 3), ntt.coset_fft(zh, log_n + 3)
+    q8 = ntt.coset_ifft([a * B.inv(b, B.R) % B.R for a, b in zip(ev_n, ev_z)], log_n + 3)
+    assert q8[:len(t)] == t and not any(q8[len(t):])
+    # 6n points: the numerator does not fit (6n + 7 >= 6n), its values on the domain still do
+    v_n, v_z = ntt.fft3(numer, log_n + 1), ntt.fft3(zh, log_n + 1)
+    w, shifts = B.fr_root_of_unity(log_n + 1), ntt.domain3_shifts(log_n + 1)
+    for k, i in [(0, 0), (1, 5), (2, 2 * n - 1)]:
+        assert v_n[k][i] == ntt.poly_eval(numer, shifts[k] * pow(w, i, B.R) % B.R)
+    q6 = ntt.ifft3([[a * B.inv(b, B.R) % B.R for a, b in zip(v_n[k], v_z[k])] for k in range(3)], log_n + 1)
+    assert q6[:len(t)] == t and not any(q6[len(t):])
+    # Z_H has period 2 along a coset of 2n points
+    assert all(v_z[k][i] == v_z[k][i % 2] for k in range(3) for i in range(2 * n))
+
+
 def test_arkworks_window_size():
     # SURVEY.md App. A.1 (ark-ec 0.3.0 ln_without_floats): values for the prover's MSM sizes
     assert msm.arkworks_window_bits(31) == 3
