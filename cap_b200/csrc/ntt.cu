@@ -14,7 +14,9 @@
 // the C-point row transforms and writes the natural-order result.  The coset shift of the
 // input is the R-entry `pre` table ((g^C)^j1); the g^-i / n scaling of coset_ifft is the
 // `post` table.  n <= 1024 is a single pass.  Inputs shorter than n are zero-extended on
-// load (the 8n-point quotient-domain transforms read only n+3 coefficients).
+// load (the quotient-domain transforms read only n+3 coefficients).  The prover's quotient
+// domain is NOT ark-poly's 8n-point coset but the 6n points g<rho> taken as three 2n-point
+// cosets (ntt3_forward / ntt3_inverse at the end of this file): same quotient polynomial.
 //
 // Roofline: a size-n transform costs (n/2) log2 n butterflies = one Montgomery product each
 // (136 IMAD.WIDE) plus <= 2 table products per element, against 2 * 32 B * n of HBM traffic
@@ -345,8 +347,6 @@ __device__ __forceinline__ void ntt_phase_butterflies(Fr (&x)[8], uint32_t t, co
     const uint32_t lo = gid & ((1u << LOG_STRIDE) - 1u);
 #pragma unroll
     for (int l = 0; l < RR; l++) {
-      constexpr int dummy = 0;
-      (void)dummy;
       const int half = 1 << (RR - 1 - l);
       const int log_m = LOG_STRIDE + RR - 1 - l;
 #pragma unroll
@@ -519,6 +519,7 @@ static void ntt_run(capgpu_ctx* ctx, unsigned log_n, const Fr* src, size_t src_l
   const uint32_t tbl_mod = coset == 2 ? 3 : 1;
   const uint32_t src_div = coset == 2 && !inverse ? 3 : 1;  // forward: the three cosets share one input
   if (coset == 2) batch *= 3;
+  CAPGPU_REQUIRE(batch <= 65535, "too many transforms in one call (the batch is the grid's y dimension)");
   NttPass p;
   p.tw = d->tile_tw[inverse ? 1 : 0];
   p.src_len = (uint32_t)src_len;
