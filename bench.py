@@ -435,11 +435,15 @@ def side_measurements(args, torch, ctxs, pk, srs, circ, wires_dev, wires, pubs, 
         "bound": "imad", "achieved": achieved, "peak": imad_peak, "unit": "G IMAD.WIDE lane-ops/s",
         "frac": achieved / imad_peak if imad_peak else None,
         # dram__bytes_read.sum + dram__bytes_write.sum per launch, averaged over the four accumulate launches of a
-        # lockstep group of 8 proofs (batches of 40 / 8 / 40 / 16 scalar vectors) in the committed capture
-        # profiles/r2_ncu_accumulate_group8_raw.csv: (267 + 62 + 291 + 108) MB / 4.  Algorithmic gather traffic of
-        # those launches is 14.1 M additions x 68 B = 962 MB on average, served mostly from L2 (the 36 MB
-        # window-shifted table is L2 resident)
-        "traffic": 182e6, "traffic_source": "profiles/r2_ncu_accumulate_group8_raw.csv (ncu --set full, the 4 accumulate launches of a lockstep group of 8: 728 MB read + written in total; the 36 MB window table stays in L2, the 3.8 GB of algorithmic gathers mostly hit it; sm__pipe_fmaheavy_cycles_active 85-90 % of elapsed)",
+        # lockstep group of 8 proofs (batches of 40 / 8 / 40 / 16 scalar vectors) in the committed capture of the final
+        # kernel, profiles/r2_ncu_accumulate_final_raw.csv: (290 + 61 + 300 + 113) MB / 4 = 191 MB, scaled linearly to this
+        # run's group size (the sorted entries read and the buckets written grow with the vectors per launch).
+        # Algorithmic gather traffic of those launches is 14.1 M additions x 68 B = 962 MB on average, served mostly
+        # from L2 (the 36 MB window-shifted table is L2 resident)
+        "traffic": 191e6 * args.group / 8,
+        "traffic_source": "profiles/r2_ncu_accumulate_final_raw.csv (ncu --set full of the final msm_accumulate<1,5>, the 4 launches of a lockstep group "
+                          "of 8: 764 MB read + written in total = 191 MB per launch, scaled by group / 8 to this run's launches; the 36 MB window table "
+                          "stays in L2 (sector hit rate 76-81 %), the 3.8 GB of algorithmic gathers mostly hit it; sm__pipe_fmaheavy_cycles_active 86-90 % of elapsed, 96 registers)",
         "peak_source": "measured in this run by capgpu_calibrate (integer multiply-add issue rate; MEASURED_PEAKS.json has no INT32 figure)",
         "fmul_microbench_gmul_per_s": calib["gfmul_per_s"],
         "frac_of_fmul_microbench": (madds_per_launch * MADD_F_MULS / sec_per_launch * 1e-9 / calib["gfmul_per_s"]) if sec_per_launch > 0 else None,
